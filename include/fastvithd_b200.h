@@ -1,0 +1,131 @@
+/* fastvithd_b200.h -- C ABI of the B200-native FastViTHD vision tower + mm_projector.
+ *
+ * Drop-in boundary for ONE path of apple/ml-fastvlm: `LlavaMetaForCausalLM.encode_images`
+ * (llava/model/llava_arch.py:141-144) == mm_projector(vision_tower(images)).  The reference has no
+ * FFI of its own (pure Python); these entry points are what a binding for that path needs and each
+ * cites the reference interface it replaces.  Plain pointers and sizes only -- no torch types.
+ *
+ * Conventions
+ *   - every function returns FVHD_OK (0) or a negative fvhd_status; fvhd_last_error(h) gives the
+ *     message (the Python wrapper raises RuntimeError with it).  There is NO CPU fallback.
+ *   - device pointers are CUDA device memory of the current device; `stream` is a cudaStream_t
+ *     passed as void* (NULL = legacy default stream).  Calls enqueue work and do not synchronise,
+ *     except the *_host entry points, which synchronise `stream` before returning.
+ *   - activations are NHWC bf16 inside the library; images enter as NCHW [B,3,R,R]
+ *     (fp32 / fp16 / bf16, processor output: mean 0, std 1, range [0,1), mobileclip_encoder.py:45-49);
+ *     tokens leave as row-major [B, (R/64)^2, C] bf16.
+ */
+#ifndef FASTVITHD_B200_H
+#define FASTVITHD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FVHD_API_VERSION 1
+
+typedef enum {
+    FVHD_OK = 0,
+    FVHD_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
+    FVHD_ERR_WEIGHTS = -2,      /* missing / mis-shaped weight tensor */
+    FVHD_ERR_CUDA = -3,         /* CUDA runtime / driver error */
+    FVHD_ERR_WORKSPACE = -4,    /* workspace missing or too small */
+    FVHD_ERR_STATE = -5         /* call order (e.g. forward before load_weights) */
+} fvhd_status;
+
+typedef enum { FVHD_F32 = 0, FVHD_F16 = 1, FVHD_BF16 = 2 } fvhd_dtype;
+
+/* Architecture constants of `fastvithd()` (mobileclip/mci.py:1454-1478); not configurable. */
+#define FVHD_EMBED_DIM 3072     /* mobileclip_l.json image_cfg.embed_dim == tower.hidden_size */
+#define FVHD_PATCH 64           /* mobileclip_l.json image_cfg.patch_size */
+
+typedef struct {
+    int image_size;             /* R: from the tower name suffix `mobileclip_l_<R>` (mobileclip_encoder.py:20); R % 64 == 0 */
+    int projector_hidden;       /* H = config.hidden_size of the LLM (multimodal_projector/builder.py:26); 0 = tower only */
+    int projector_depth;        /* N of `mlp{N}x_gelu` (builder.py:23-30); 1 or 2; ignored when projector_hidden == 0 */
+    int max_batch;              /* images processed per internal pass; larger batches are chunked */
+} fvhd_config;
+
+/* One packed weight tensor (produced by the host-side packer from the reference state-dict keys
+ * `model.vision_tower.vision_tower.model.*` / `model.mm_projector.{0,2}.*`). */
+typedef struct {
+    const char* name;           /* packed name, e.g. "network.2.5.fc1.w" */
+    const void* data;           /* device pointer, 16-byte aligned */
+    int dtype;                  /* FVHD_F32 or FVHD_BF16 */
+    int64_t numel;
+} fvhd_tensor;
+
+typedef struct fvhd_handle_s* fvhd_handle;
+
+/* replaces: MobileCLIPVisionTower.__init__ / load_model (mobileclip_encoder.py:14-58) and
+ * build_vision_projector (multimodal_projector/builder.py:17-35): builds the execution plan. */
+int fvhd_create(const fvhd_config* cfg, fvhd_handle* out);
+int fvhd_destroy(fvhd_handle h);
+const char* fvhd_last_error(fvhd_handle h);    /* h may be NULL: error of the last failed fvhd_create */
+int fvhd_api_version(void);
+
+/* Names of the packed tensors the plan requires, in order (for the packer / for error reporting). */
+int fvhd_num_weights(fvhd_handle h);
+int fvhd_weight_spec(fvhd_handle h, int i, const char** name, int* dtype, int64_t* numel);
+
+/* replaces: from_pretrained / load_state_dict of tower + projector (llava/model/builder.py:131,169-174).
+ * The caller keeps ownership of the device buffers and must keep them alive. */
+int fvhd_load_weights(fvhd_handle h, const fvhd_tensor* table, int n);
+
+/* Caller-owned scratch.  Bytes needed for `batch` images per pass (batch <= cfg.max_batch). */
+size_t fvhd_workspace_bytes(fvhd_handle h, int batch);
+int fvhd_set_workspace(fvhd_handle h, void* dptr, size_t bytes);
+
+/* replaces: MobileCLIPVisionTower.forward_images + feature_select (mobileclip_encoder.py:60-88) and,
+ * when `projected` != NULL, mm_projector (multimodal_projector/builder.py:23-30) == encode_images
+ * (llava_arch.py:141-144).
+ *   images     device, NCHW [B,3,R,R] of `img_dtype`
+ *   tokens     device, [B,(R/64)^2,3072] bf16, or NULL
+ *   projected  device, [B,(R/64)^2,H] bf16, or NULL (requires projector_hidden > 0) */
+int fvhd_forward(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch,
+                 void* tokens, void* projected);
+
+/* Same call with HOST buffers: H2D of the images, the forward, D2H of the result, one stream sync.
+ * `host_out` receives `projected` when the plan has a projector, else `tokens` (bf16). */
+int fvhd_encode_images_host(fvhd_handle h, void* stream, const void* host_images, int img_dtype, int batch,
+                            void* host_out);
+
+/* Geometry helpers (mobileclip_encoder.py:103-116). */
+int fvhd_num_tokens(fvhd_handle h);             /* (R/64)^2 == tower.num_patches */
+int fvhd_out_dim(fvhd_handle h);                /* H if projector else 3072 */
+
+/* ---- unit-level access (parity tests and per-unit roofline; units follow the reference modules:
+ * "stem", "network.<i>.<b>" / "network.<i>", "conv_exp", "projector") ---- */
+int fvhd_num_units(fvhd_handle h);
+/* in/out element counts are per image; activations NHWC bf16 ([H*W, C] row-major). */
+int fvhd_unit_info(fvhd_handle h, int u, const char** name, int64_t* in_elems, int64_t* out_elems,
+                   int* out_h, int* out_w, int* out_c, double* flops_per_image, double* min_bytes_per_image);
+/* Run units [first, last] on `batch` images: `in` is the bf16 NHWC input of unit `first`
+ * (for first == 0 the NCHW image of `img_dtype`), `out` receives the bf16 output of unit `last`. */
+int fvhd_run_units(fvhd_handle h, void* stream, int first, int last, const void* in, int img_dtype,
+                   int batch, void* out);
+/* Forward with a cudaEvent around every unit; ms[u] = milliseconds of unit u (synchronises). */
+int fvhd_profile_units(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch,
+                       float* ms, int n_ms);
+/* Kernel-level view of the plan for `batch` images per pass: one step == one kernel launch.
+ * kernel = __global__ function name, unit = owning unit, flops/bytes = ALGORITHMIC work of that launch
+ * (2*MACs; operands read once + result written once).  fvhd_profile_steps brackets every launch with
+ * cudaEvents on `stream` (ms[i], synchronises) -- the live per-kernel times bench.py's roofline uses. */
+int fvhd_num_steps(fvhd_handle h, int batch);
+int fvhd_step_info(fvhd_handle h, int batch, int i, const char** kernel, int* unit, double* flops, double* bytes);
+int fvhd_profile_steps(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch,
+                       float* ms, int n_ms);
+/* Number of kernel launches one forward of `batch` images enqueues. */
+int fvhd_launches_per_forward(fvhd_handle h, int batch);
+
+/* Stand-alone GEMM entry (tests): D[M,N] = act(A[M,K] W[N,K]^T + bias) + residual, bf16. */
+int fvhd_gemm(fvhd_handle h, void* stream, const void* A, const void* W, const void* bias, const void* residual,
+              void* D, int M, int N, int K, int act);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTVITHD_B200_H */

@@ -1,0 +1,22 @@
+"""fastvithd-b200: B200-native FastViTHD vision tower + mm_projector for apple/ml-fastvlm.
+
+Host side (Python/PyTorch plumbing) of `libfastvithd_b200.so` (hand-written sm_100a CUDA behind the
+C ABI in include/fastvithd_b200.h).  Mirrors the reference's plugin surface for ONE path,
+`LlavaMetaForCausalLM.encode_images` (llava/model/llava_arch.py:141-144):
+
+    build_vision_tower      <- llava/model/multimodal_encoder/builder.py:6-19
+    FastViTHDVisionTower    <- llava/model/multimodal_encoder/mobileclip_encoder.py:13-116
+    build_vision_projector  <- llava/model/multimodal_projector/builder.py:17-35
+    encode_images / EncodeImagesMixin / patch_llava  <- llava/model/llava_arch.py:141-144
+
+There is no CPU fallback: importing works anywhere, computing requires a B200 and the built library.
+"""
+from .lib import library_path, load_library, FvhdError  # noqa: F401
+from .arch import reference_param_specs, projector_param_specs  # noqa: F401
+from .packer import pack_tower, pack_projector  # noqa: F401
+from .engine import Engine  # noqa: F401
+from .tower import FastViTHDVisionTower, build_vision_tower  # noqa: F401
+from .projector import FastVLMProjector, build_vision_projector  # noqa: F401
+from .glue import encode_images, EncodeImagesMixin, patch_llava  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,817 @@
+// libfastvithd_b200.so -- C ABI (include/fastvithd_b200.h) over the sm_100a kernels.
+//
+// Host side of the library: architecture plan of `fastvithd()` (mci.py:1454-1478), packed-weight
+// table, workspace carving, TMA descriptor cache, launch sequence.  No torch, no CPU compute path.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/fastvithd_b200.h"
+#include "dwconv.cuh"
+#include "gemm_tcgen05.cuh"
+#include "stem_attn_se.cuh"
+
+using namespace fvhd;
+
+namespace {
+
+const int kLayers[5] = {2, 12, 24, 4, 2};           // mci.py:1457
+const int kDims[5] = {96, 192, 384, 768, 1536};     // mci.py:1458
+const int kSeRd = 192;                               // int(3072 * 0.0625), mci.py:49
+std::string g_create_error;
+
+struct WeightSpec { std::string name; int dtype; int64_t numel; };
+
+struct RunCtx {
+    const void* images; int img_dtype;
+    void* final_out;            // destination of the last unit's output when it is user memory (or nullptr)
+};
+typedef std::function<cudaError_t(cudaStream_t, const RunCtx&)> Step;
+
+struct UnitDesc {
+    std::string name;
+    int kind;                   // 0 stem, 1 repmixer, 2 down, 3 cpe, 4 attn, 5 conv_exp, 6 projector
+    int stage, block;
+    int cin, cout, hin, win, hout, wout;
+    int64_t in_elems, out_elems;
+    double flops, min_bytes;
+    std::string prefix;         // packed weight prefix
+};
+
+struct Plan {                   // launch sequence for one batch size
+    int batch = 0;
+    std::vector<Step> steps;
+    std::vector<std::pair<int, int>> unit_steps;   // [begin, end) per unit
+    std::vector<bf16*> unit_in, unit_out;          // workspace buffers per unit
+    struct Info { const char* kernel; int unit; double flops; double bytes; };
+    std::vector<Info> info;                        // one per step (== one kernel launch)
+    void add(const Step& s, const char* kernel, int unit, double flops, double bytes) {
+        steps.push_back(s);
+        info.push_back({kernel, unit, flops, bytes});
+    }
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct fvhd_handle_s {
+    fvhd_config cfg;
+    std::string err;
+    int R = 0, ntok = 0;
+    std::vector<WeightSpec> specs;
+    std::vector<UnitDesc> units;
+    std::map<std::string, const void*> wptr;
+    bool loaded = false;
+    bool cuda_ready = false;
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    EncodeTiledFn encode = nullptr;
+    std::map<int, Plan> plans;
+    int64_t act0 = 0;           // elements of the largest activation per image: (R/4)^2 * 96
+    void *stage_in = nullptr, *stage_out = nullptr;   // fvhd_encode_images_host device staging
+    size_t stage_in_bytes = 0, stage_out_bytes = 0;
+};
+
+namespace {
+
+int fail(fvhd_handle h, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                      \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+void add_spec(fvhd_handle h, const std::string& n, int dt, int64_t numel) { h->specs.push_back({n, dt, numel}); }
+
+void add_convffn_specs(fvhd_handle h, const std::string& p, int c) {
+    add_spec(h, p + "dw.w", FVHD_F32, 49LL * c);
+    add_spec(h, p + "dw.b", FVHD_F32, c);
+    add_spec(h, p + "fc1.w", FVHD_BF16, 4LL * c * c);
+    add_spec(h, p + "fc1.b", FVHD_F32, 4LL * c);
+    add_spec(h, p + "fc2.w", FVHD_BF16, 4LL * c * c);
+    add_spec(h, p + "fc2.b", FVHD_F32, c);
+}
+
+// Architecture walk of FastViT.__init__ (mci.py:1353-1411) for `fastvithd`.
+void build_arch(fvhd_handle h) {
+    const int R = h->R;
+    const int H = h->cfg.projector_hidden;
+    int hw = R / 4;
+    h->act0 = (int64_t)hw * hw * 96;
+    {   // convolutional_stem (mci.py:553-603)
+        UnitDesc u{};
+        u.name = "stem"; u.kind = 0; u.cin = 3; u.cout = 96; u.hin = u.win = R; u.hout = u.wout = hw;
+        u.in_elems = 3LL * R * R; u.out_elems = (int64_t)hw * hw * 96;
+        const double macs = (double)(R / 2) * (R / 2) * 96 * 27 + (double)hw * hw * 96 * 9 + (double)hw * hw * 96 * 96;
+        u.flops = 2 * macs;
+        u.min_bytes = (u.in_elems + u.out_elems) * 2.0 + (27 * 96 + 9 * 96) * 4 + 96 * 96 * 2;
+        u.prefix = "stem.";
+        h->units.push_back(u);
+        add_spec(h, "stem.w0", FVHD_F32, 27 * 96); add_spec(h, "stem.b0", FVHD_F32, 96);
+        add_spec(h, "stem.w1", FVHD_F32, 9 * 96);  add_spec(h, "stem.b1", FVHD_F32, 96);
+        add_spec(h, "stem.w2", FVHD_BF16, 96 * 96); add_spec(h, "stem.b2", FVHD_F32, 96);
+    }
+    int idx = 0;
+    for (int i = 0; i < 5; ++i) {
+        const int c = kDims[i];
+        const int64_t px = (int64_t)hw * hw;
+        if (i >= 3) {   // RepCPE (mci.py:971-980)
+            UnitDesc u{};
+            u.name = "network." + std::to_string(idx); u.kind = 3; u.stage = i;
+            u.cin = u.cout = c; u.hin = u.win = u.hout = u.wout = hw;
+            u.in_elems = u.out_elems = px * c;
+            u.flops = 2.0 * px * c * 49; u.min_bytes = 4.0 * px * c + 50.0 * c * 4;
+            u.prefix = u.name + ".";
+            h->units.push_back(u);
+            add_spec(h, u.prefix + "dw.w", FVHD_F32, 49LL * c); add_spec(h, u.prefix + "dw.b", FVHD_F32, c);
+            ++idx;
+        }
+        for (int b = 0; b < kLayers[i]; ++b) {
+            UnitDesc u{};
+            u.name = "network." + std::to_string(idx) + "." + std::to_string(b);
+            u.stage = i; u.block = b; u.cin = u.cout = c; u.hin = u.win = u.hout = u.wout = hw;
+            u.in_elems = u.out_elems = px * c;
+            u.prefix = u.name + ".";
+            double macs = (double)px * c * 49 + 2.0 * px * c * 4 * c;
+            double wbytes = 8.0 * c * c * 2 + (49.0 * c + 6 * c) * 4;
+            if (i < 3) {    // RepMixerBlock (mci.py:1042-1113)
+                u.kind = 1;
+                macs += (double)px * c * 9;
+                wbytes += 10.0 * c * 4;
+                add_spec(h, u.prefix + "mix.w", FVHD_F32, 9LL * c); add_spec(h, u.prefix + "mix.b", FVHD_F32, c);
+            } else {        // AttentionBlock (mci.py:1116-1192)
+                u.kind = 4;
+                macs += (double)px * c * 3 * c + (double)px * c * c + 2.0 * px * px * c;
+                wbytes += 4.0 * c * c * 2 + 3.0 * c * 4;
+                add_spec(h, u.prefix + "ln.w", FVHD_F32, c); add_spec(h, u.prefix + "ln.b", FVHD_F32, c);
+                add_spec(h, u.prefix + "qkv.w", FVHD_BF16, 3LL * c * c);
+                add_spec(h, u.prefix + "proj.w", FVHD_BF16, (int64_t)c * c); add_spec(h, u.prefix + "proj.b", FVHD_F32, c);
+            }
+            add_convffn_specs(h, u.prefix, c);
+            u.flops = 2 * macs; u.min_bytes = 4.0 * px * c + wbytes;
+            h->units.push_back(u);
+        }
+        ++idx;
+        if (i < 4) {    // PatchEmbed (mci.py:688-741)
+            const int co = kDims[i + 1];
+            UnitDesc u{};
+            u.name = "network." + std::to_string(idx); u.kind = 2; u.stage = i;
+            u.cin = c; u.cout = co; u.hin = u.win = hw; u.hout = u.wout = hw / 2;
+            const int64_t opx = (int64_t)(hw / 2) * (hw / 2);
+            u.in_elems = px * c; u.out_elems = opx * co;
+            u.flops = 2.0 * (opx * co * 49.0 + (double)opx * co * co);
+            u.min_bytes = 2.0 * (u.in_elems + u.out_elems) + (double)co * co * 2 + 51.0 * co * 4;
+            u.prefix = u.name + ".";
+            h->units.push_back(u);
+            add_spec(h, u.prefix + "dw.w", FVHD_F32, 49LL * co); add_spec(h, u.prefix + "dw.b", FVHD_F32, co);
+            add_spec(h, u.prefix + "pw.w", FVHD_BF16, (int64_t)co * co); add_spec(h, u.prefix + "pw.b", FVHD_F32, co);
+            ++idx;
+            hw /= 2;
+        }
+    }
+    {   // conv_exp + SE (mci.py:1401-1411, 42-81) -> tokens [HW, 3072] (feature_select, mobileclip_encoder.py:60-68)
+        UnitDesc u{};
+        const int64_t px = (int64_t)hw * hw;
+        u.name = "conv_exp"; u.kind = 5; u.cin = 1536; u.cout = 3072; u.hin = u.win = u.hout = u.wout = hw;
+        u.in_elems = px * 1536; u.out_elems = px * 3072;
+        u.flops = 2.0 * (px * 3072.0 * 9 + 2.0 * 3072 * kSeRd);
+        u.min_bytes = 2.0 * (u.in_elems + u.out_elems) + 2.0 * 3072 * kSeRd * 2 + 3072.0 * 11 * 4;
+        u.prefix = "conv_exp.";
+        h->units.push_back(u);
+        add_spec(h, "conv_exp.dw.w", FVHD_F32, 9 * 3072); add_spec(h, "conv_exp.dw.b", FVHD_F32, 3072);
+        add_spec(h, "conv_exp.se.r.w", FVHD_BF16, (int64_t)kSeRd * 3072); add_spec(h, "conv_exp.se.r.b", FVHD_F32, kSeRd);
+        add_spec(h, "conv_exp.se.e.w", FVHD_BF16, (int64_t)3072 * kSeRd); add_spec(h, "conv_exp.se.e.b", FVHD_F32, 3072);
+    }
+    if (H > 0) {    // mlp{N}x_gelu (multimodal_projector/builder.py:23-30)
+        UnitDesc u{};
+        const int64_t px = (int64_t)hw * hw;
+        u.name = "projector"; u.kind = 6; u.cin = 3072; u.cout = H; u.hin = u.win = u.hout = u.wout = hw;
+        u.in_elems = px * 3072; u.out_elems = px * H;
+        double macs = (double)px * 3072 * H, wb = 3072.0 * H * 2 + H * 4.0;
+        add_spec(h, "projector.0.w", FVHD_BF16, 3072LL * H); add_spec(h, "projector.0.b", FVHD_F32, H);
+        if (h->cfg.projector_depth == 2) {
+            macs += (double)px * H * H; wb += (double)H * H * 2 + H * 4.0;
+            add_spec(h, "projector.2.w", FVHD_BF16, (int64_t)H * H); add_spec(h, "projector.2.b", FVHD_F32, H);
+        }
+        u.flops = 2 * macs; u.min_bytes = 2.0 * (u.in_elems + u.out_elems) + wb;
+        u.prefix = "projector.";
+        h->units.push_back(u);
+    }
+}
+
+// ------------------------------------------------------------------ workspace carving
+struct Buffers {
+    bf16 *X0, *X1, *Y, *Z, *T1, *H4;
+    float *pooled, *sr;
+};
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+size_t workspace_bytes(fvhd_handle h, int batch) {
+    const size_t a = align_up((size_t)h->act0 * batch * 2, 1024);
+    return 9 * a + align_up((size_t)batch * 3072 * 4, 1024) + align_up((size_t)batch * kSeRd * 4, 1024) + 1024;
+}
+Buffers carve(fvhd_handle h, int batch) {
+    const size_t a = align_up((size_t)h->act0 * batch * 2, 1024);
+    uint8_t* p = reinterpret_cast<uint8_t*>(align_up((size_t)h->ws, 1024));
+    Buffers b;
+    b.X0 = (bf16*)p; p += a;
+    b.X1 = (bf16*)p; p += a;
+    b.Y = (bf16*)p; p += a;
+    b.Z = (bf16*)p; p += a;
+    b.T1 = (bf16*)p; p += a;
+    b.H4 = (bf16*)p; p += 4 * a;
+    b.pooled = (float*)p; p += align_up((size_t)batch * 3072 * 4, 1024);
+    b.sr = (float*)p;
+    return b;
+}
+
+// ------------------------------------------------------------------ CUDA lazy init
+template <typename K> cudaError_t set_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+int ensure_cuda(fvhd_handle h) {
+    if (h->cuda_ready) return FVHD_OK;
+    int dev = 0;
+    CUDA_TRY(h, cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CUDA_TRY(h, cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return fail(h, FVHD_ERR_CUDA, "device is sm_%d%d; this library is sm_100a only", prop.major, prop.minor);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_TRY(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(h, FVHD_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    CUDA_TRY(h, set_smem(gemm_bf16_tcgen05_kernel, 227 * 1024));
+    CUDA_TRY(h, set_smem(repmixer_dw_kernel, MixCfg::SMEM));
+    CUDA_TRY(h, set_smem(dwconv_kernel<7, 1, 1, 0, 16, 16, 8>, DwCfg<7, 1, 1, 16, 16>::SMEM));
+    CUDA_TRY(h, set_smem(dwconv_kernel<7, 2, 2, 1, 8, 8, 4>, DwCfg<7, 2, 2, 8, 8>::SMEM));
+    CUDA_TRY(h, set_smem(dwconv_kernel<3, 1, 2, 0, 16, 16, 8>, DwCfg<3, 1, 2, 16, 16>::SMEM));
+    CUDA_TRY(h, set_smem(stem_kernel<float>, STEM_SMEM));
+    CUDA_TRY(h, set_smem(stem_kernel<__half>, STEM_SMEM));
+    CUDA_TRY(h, set_smem(stem_kernel<bf16>, STEM_SMEM));
+    h->cuda_ready = true;
+    return FVHD_OK;
+}
+
+// bf16 row-major [rows, K] matrix with row pitch `ld` elements -> 2-D tensor map, box {64, box_rows}, 128-B swizzle.
+int make_tmap(fvhd_handle h, CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+    if (((uintptr_t)ptr & 15) || (ld * 2) % 16) return fail(h, FVHD_ERR_INVALID, "TMA operand must be 16-B aligned (ptr %p, ld %lld)", ptr, (long long)ld);
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, FVHD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld ld=%lld box=%d", (int)r,
+                                       (long long)rows, (long long)K, (long long)ld, box_rows);
+    return FVHD_OK;
+}
+
+int pick_bn(int N) {
+    if (N % 128 == 0) return 128;
+    if (N % 96 == 0 && N <= 256) return 96;
+    if (N % 64 == 0) return 64;
+    if (N >= 128) return 128;
+    return ((N + 31) / 32) * 32;
+}
+
+// Build one GEMM launch step.  D may be nullptr => taken from RunCtx.final_out at launch time.
+int make_gemm_step(fvhd_handle h, Step* out, const bf16* A, int lda, const bf16* W, const float* bias, const bf16* residual, int ldr,
+                   bf16* D, int ldd, int M, int N, int K, int act) {
+    if (N % 8 || K % 8) return fail(h, FVHD_ERR_INVALID, "GEMM N (%d) and K (%d) must be multiples of 8", N, K);
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K;
+    p.BN = pick_bn(N);
+    const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+    p.stages = num_kb < 3 ? num_kb : 3;
+    p.D = D; p.ldd = ldd; p.bias = bias; p.residual = residual; p.ldr = ldr; p.act = act;
+    CUtensorMap ta, tb;
+    int rc;
+    if ((rc = make_tmap(h, &ta, A, M, K, lda, GEMM_BM)) != FVHD_OK) return rc;
+    if ((rc = make_tmap(h, &tb, W, N, K, K, p.BN)) != FVHD_OK) return rc;
+    const dim3 grid((N + p.BN - 1) / p.BN, (M + GEMM_BM - 1) / GEMM_BM);
+    const size_t smem = gemm_smem_bytes(p.BN, p.stages);
+    *out = [=](cudaStream_t s, const RunCtx& ctx) -> cudaError_t {
+        GemmParams q = p;
+        if (!q.D) q.D = reinterpret_cast<bf16*>(ctx.final_out);
+        gemm_bf16_tcgen05_kernel<<<grid, GEMM_THREADS, smem, s>>>(ta, tb, q);
+        return cudaGetLastError();
+    };
+    return FVHD_OK;
+}
+
+template <int KS, int S, int MULT, int ACT, int TOH, int TOW, int SW>
+Step make_dw_step(const bf16* in, bf16* out, const float* w, const float* b, int batch, int H, int W, int C) {
+    const int Ho = (H + 2 * (KS / 2) - KS) / S + 1, Wo = (W + 2 * (KS / 2) - KS) / S + 1;
+    const int tx = (Wo + TOW - 1) / TOW, ty = (Ho + TOH - 1) / TOH;
+    const dim3 grid(tx * ty, C / DW_CG, batch);
+    const size_t smem = DwCfg<KS, S, MULT, TOH, TOW>::SMEM;
+    return [=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+        dwconv_kernel<KS, S, MULT, ACT, TOH, TOW, SW><<<grid, DW_THREADS, smem, s>>>(in, out, w, b, H, W, C, Ho, Wo, tx);
+        return cudaGetLastError();
+    };
+}
+
+const float* WF(fvhd_handle h, const std::string& n) { return reinterpret_cast<const float*>(h->wptr.at(n)); }
+const bf16* WB(fvhd_handle h, const std::string& n) { return reinterpret_cast<const bf16*>(h->wptr.at(n)); }
+
+const char* kGemm = "gemm_bf16_tcgen05_kernel";
+double gemm_flops(double M, double N, double K) { return 2.0 * M * N * K; }
+double gemm_bytes(double M, double N, double K, bool res) { return 2.0 * (M * K + N * K + M * N * (res ? 2 : 1)) + 4.0 * N; }
+
+int add_gemm(fvhd_handle h, Plan& pl, int unit, const bf16* A, int lda, const bf16* W, const float* bias, const bf16* residual, int ldr,
+             bf16* D, int ldd, int M, int N, int K, int act) {
+    Step g;
+    int rc = make_gemm_step(h, &g, A, lda, W, bias, residual, ldr, D, ldd, M, N, K, act);
+    if (rc != FVHD_OK) return rc;
+    pl.add(g, kGemm, unit, gemm_flops(M, N, K), gemm_bytes(M, N, K, residual != nullptr));
+    return FVHD_OK;
+}
+
+int add_convffn_steps(fvhd_handle h, Plan& pl, int unit, const std::string& p, const Buffers& bf, const bf16* z, const bf16* resid, bf16* out, int M, int c) {
+    int rc;
+    if ((rc = add_gemm(h, pl, unit, z, c, WB(h, p + "fc1.w"), WF(h, p + "fc1.b"), nullptr, 0, bf.H4, 4 * c, M, 4 * c, c, 1)) != FVHD_OK) return rc;
+    return add_gemm(h, pl, unit, bf.H4, 4 * c, WB(h, p + "fc2.w"), WF(h, p + "fc2.b"), resid, c, out, c, M, c, 4 * c, 0);
+}
+
+int build_plan(fvhd_handle h, int batch, Plan& pl) {
+    pl = Plan();
+    pl.batch = batch;
+    const Buffers bf = carve(h, batch);
+    bf16* cur = bf.X0;
+    bf16* nxt = bf.X1;
+    int rc;
+    const size_t nunits = h->units.size();
+    for (size_t ui = 0; ui < nunits; ++ui) {
+        const UnitDesc& u = h->units[ui];
+        const int U = (int)ui;
+        const int begin = (int)pl.steps.size();
+        const std::string& p = u.prefix;
+        const int c = u.cin, H = u.hin, W = u.win;
+        const int M = batch * u.hout * u.wout;
+        const double Md = (double)M;
+        const bool last = ui + 1 == nunits;
+        bf16* in = cur;
+        bf16* out = nxt;
+        switch (u.kind) {
+        case 0: {   // stem: fused conv0+dw1 -> T1, then 1x1+GELU GEMM
+            const float *w0 = WF(h, "stem.w0"), *b0 = WF(h, "stem.b0"), *w1 = WF(h, "stem.w1"), *b1 = WF(h, "stem.b1");
+            const int R = h->R, tiles = (R / 4 + STEM_TO - 1) / STEM_TO;
+            const dim3 grid(tiles * tiles, 1, batch);
+            bf16* t0 = bf.T1;
+            pl.add([=](cudaStream_t s, const RunCtx& ctx) -> cudaError_t {
+                if (ctx.img_dtype == FVHD_F32) stem_kernel<float><<<grid, STEM_THREADS, STEM_SMEM, s>>>((const float*)ctx.images, t0, w0, b0, w1, b1, R, tiles);
+                else if (ctx.img_dtype == FVHD_F16) stem_kernel<__half><<<grid, STEM_THREADS, STEM_SMEM, s>>>((const __half*)ctx.images, t0, w0, b0, w1, b1, R, tiles);
+                else stem_kernel<bf16><<<grid, STEM_THREADS, STEM_SMEM, s>>>((const bf16*)ctx.images, t0, w0, b0, w1, b1, R, tiles);
+                return cudaGetLastError();
+            }, "stem_kernel", U, 2.0 * batch * ((double)(R / 2) * (R / 2) * 96 * 27 + (double)(R / 4) * (R / 4) * 96 * 9),
+               (double)batch * (3.0 * R * R * 2 + (double)(R / 4) * (R / 4) * 96 * 2));
+            if ((rc = add_gemm(h, pl, U, t0, 96, WB(h, "stem.w2"), WF(h, "stem.b2"), nullptr, 0, out, 96, M, 96, 96, 1)) != FVHD_OK) return rc;
+            in = nullptr;
+            break;
+        }
+        case 1: {   // RepMixerBlock: fused dw3x3 -> y, dw7x7(+BN) -> z ; fc1+GELU ; fc2 (+layer scale folded) + y
+            const float *w3 = WF(h, p + "mix.w"), *b3 = WF(h, p + "mix.b"), *w7 = WF(h, p + "dw.w"), *b7 = WF(h, p + "dw.b");
+            const int tx = (W + MixCfg::TO - 1) / MixCfg::TO, ty = (H + MixCfg::TO - 1) / MixCfg::TO;
+            const dim3 grid(tx * ty, c / DW_CG, batch);
+            bf16 *y = bf.Y, *z = bf.Z;
+            pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+                repmixer_dw_kernel<<<grid, DW_THREADS, MixCfg::SMEM, s>>>(in, y, z, w3, b3, w7, b7, H, W, c, tx);
+                return cudaGetLastError();
+            }, "repmixer_dw_kernel", U, 2.0 * Md * c * 58, 3.0 * Md * c * 2);
+            if ((rc = add_convffn_steps(h, pl, U, p, bf, z, y, out, M, c)) != FVHD_OK) return rc;
+            break;
+        }
+        case 2: {   // PatchEmbed: dw7x7 s2 (x2 channels) + GELU ; 1x1 + GELU
+            pl.add(make_dw_step<7, 2, 2, 1, 8, 8, 4>(in, bf.T1, WF(h, p + "dw.w"), WF(h, p + "dw.b"), batch, H, W, c), "dwconv_kernel<7,2,2>", U,
+                   2.0 * Md * u.cout * 49, 2.0 * ((double)batch * u.in_elems + Md * u.cout));
+            if ((rc = add_gemm(h, pl, U, bf.T1, u.cout, WB(h, p + "pw.w"), WF(h, p + "pw.b"), nullptr, 0, out, u.cout, M, u.cout, u.cout, 1)) != FVHD_OK) return rc;
+            break;
+        }
+        case 3:     // RepCPE: dw7x7 + bias (identity folded into the centre tap)
+            pl.add(make_dw_step<7, 1, 1, 0, 16, 16, 8>(in, out, WF(h, p + "dw.w"), WF(h, p + "dw.b"), batch, H, W, c), "dwconv_kernel<7,1,1>", U,
+                   2.0 * Md * c * 49, 4.0 * Md * c);
+            break;
+        case 4: {   // AttentionBlock
+            const int N = H * W;
+            const float *lw = WF(h, p + "ln.w"), *lb = WF(h, p + "ln.b");
+            bf16 *t1 = bf.T1, *qkv = bf.H4, *x1 = bf.Y;
+            const int lngrid = (M + 7) / 8;
+            if (c != 768 && c != 1536) return fail(h, FVHD_ERR_INVALID, "LayerNorm kernel expects C in {768,1536}, got %d", c);
+            pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+                if (c == 768) layernorm_channel_kernel<3><<<lngrid, 256, 0, s>>>(in, t1, lw, lb, M, 1e-5f);
+                else layernorm_channel_kernel<6><<<lngrid, 256, 0, s>>>(in, t1, lw, lb, M, 1e-5f);
+                return cudaGetLastError();
+            }, "layernorm_channel_kernel", U, 0.0, 4.0 * Md * c);
+            if ((rc = add_gemm(h, pl, U, t1, c, WB(h, p + "qkv.w"), nullptr, nullptr, 0, qkv, 3 * c, M, 3 * c, c, 0)) != FVHD_OK) return rc;
+            const dim3 agrid((N + 63) / 64, c / 32, batch);
+            const float sl2 = 0.17677669529663687f * 1.4426950408889634f;   // 32^-0.5 * log2(e)
+            pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+                attention_kernel<<<agrid, 128, 0, s>>>(qkv, t1, N, c, sl2);
+                return cudaGetLastError();
+            }, "attention_kernel", U, 4.0 * batch * (double)N * N * c, 8.0 * Md * c);
+            if ((rc = add_gemm(h, pl, U, t1, c, WB(h, p + "proj.w"), WF(h, p + "proj.b"), in, c, x1, c, M, c, c, 0)) != FVHD_OK) return rc;
+            pl.add(make_dw_step<7, 1, 1, 0, 16, 16, 8>(x1, bf.Z, WF(h, p + "dw.w"), WF(h, p + "dw.b"), batch, H, W, c), "dwconv_kernel<7,1,1>", U,
+                   2.0 * Md * c * 49, 4.0 * Md * c);
+            if ((rc = add_convffn_steps(h, pl, U, p, bf, bf.Z, x1, out, M, c)) != FVHD_OK) return rc;
+            break;
+        }
+        case 5: {   // conv_exp: dw3x3 (x2 channels) -> SE -> GELU -> tokens
+            const int HW = H * W;
+            bf16* cexp = bf.T1;
+            pl.add(make_dw_step<3, 1, 2, 0, 16, 16, 8>(in, cexp, WF(h, p + "dw.w"), WF(h, p + "dw.b"), batch, H, W, c), "dwconv_kernel<3,1,2>", U,
+                   2.0 * Md * 3072 * 9, 2.0 * Md * (1536 + 3072));
+            float *pooled = bf.pooled, *sr = bf.sr;
+            const bf16 *wr = WB(h, p + "se.r.w"), *we = WB(h, p + "se.e.w");
+            const float *br = WF(h, p + "se.r.b"), *be = WF(h, p + "se.e.b");
+            bf16* dst = last ? nullptr : out;
+            pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+                se_pool_kernel<<<dim3(3072 / 64, batch), 256, 0, s>>>(cexp, pooled, HW, 3072);
+                return cudaGetLastError();
+            }, "se_pool_kernel", U, 0.0, 2.0 * Md * 3072);
+            pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+                se_reduce_kernel<<<dim3(kSeRd / 8, batch), 256, 0, s>>>(pooled, wr, br, sr, 3072, kSeRd);
+                return cudaGetLastError();
+            }, "se_reduce_kernel", U, 2.0 * batch * 3072 * kSeRd, 2.0 * 3072 * kSeRd);
+            pl.add([=](cudaStream_t s, const RunCtx& ctx) -> cudaError_t {
+                bf16* d = dst ? dst : reinterpret_cast<bf16*>(ctx.final_out);
+                se_expand_scale_gelu_kernel<<<dim3(3072 / 128, batch), 256, 0, s>>>(cexp, sr, we, be, d, HW, 3072, kSeRd);
+                return cudaGetLastError();
+            }, "se_expand_scale_gelu_kernel", U, 2.0 * batch * 3072 * kSeRd, 4.0 * Md * 3072 + 2.0 * 3072 * kSeRd);
+            break;
+        }
+        case 6: {   // projector
+            const int Hd = u.cout;
+            if (h->cfg.projector_depth == 2) {
+                if ((rc = add_gemm(h, pl, U, in, 3072, WB(h, "projector.0.w"), WF(h, "projector.0.b"), nullptr, 0, bf.T1, Hd, M, Hd, 3072, 1)) != FVHD_OK) return rc;
+                if ((rc = add_gemm(h, pl, U, bf.T1, Hd, WB(h, "projector.2.w"), WF(h, "projector.2.b"), nullptr, 0, nullptr, Hd, M, Hd, Hd, 0)) != FVHD_OK) return rc;
+            } else {
+                if ((rc = add_gemm(h, pl, U, in, 3072, WB(h, "projector.0.w"), WF(h, "projector.0.b"), nullptr, 0, nullptr, Hd, M, Hd, 3072, 0)) != FVHD_OK) return rc;
+            }
+            break;
+        }
+        default:
+            return fail(h, FVHD_ERR_INVALID, "unknown unit kind %d", u.kind);
+        }
+        pl.unit_steps.push_back({begin, (int)pl.steps.size()});
+        pl.unit_in.push_back(in);
+        pl.unit_out.push_back(out);
+        cur = out;
+        nxt = (out == bf.X0) ? bf.X1 : bf.X0;
+    }
+    return FVHD_OK;
+}
+
+int get_plan(fvhd_handle h, int batch, Plan** out) {
+    auto it = h->plans.find(batch);
+    if (it == h->plans.end()) {
+        Plan pl;
+        int rc = build_plan(h, batch, pl);
+        if (rc != FVHD_OK) return rc;
+        it = h->plans.emplace(batch, std::move(pl)).first;
+    }
+    *out = &it->second;
+    return FVHD_OK;
+}
+
+int check_ready(fvhd_handle h, int batch) {
+    if (!h) return FVHD_ERR_INVALID;
+    if (!h->loaded) return fail(h, FVHD_ERR_STATE, "fvhd_load_weights has not been called");
+    if (batch < 1) return fail(h, FVHD_ERR_INVALID, "batch must be >= 1 (got %d)", batch);
+    const int bc = batch < h->cfg.max_batch ? batch : h->cfg.max_batch;
+    if (!h->ws || h->ws_bytes < workspace_bytes(h, bc))
+        return fail(h, FVHD_ERR_WORKSPACE, "workspace %zu B < required %zu B for %d images per pass", h->ws_bytes, workspace_bytes(h, bc), bc);
+    return ensure_cuda(h);
+}
+
+size_t dtype_size(int dt) { return dt == FVHD_F32 ? 4 : 2; }
+
+// Run steps [s0, s1) of a plan.
+int run_steps(fvhd_handle h, Plan& pl, int s0, int s1, cudaStream_t st, const RunCtx& ctx) {
+    for (int i = s0; i < s1; ++i) {
+        cudaError_t e = pl.steps[i](st, ctx);
+        if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "launch of step %d failed: %s", i, cudaGetErrorString(e));
+    }
+    return FVHD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fvhd_api_version(void) { return FVHD_API_VERSION; }
+
+const char* fvhd_last_error(fvhd_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int fvhd_create(const fvhd_config* cfg, fvhd_handle* out) {
+    if (!cfg || !out) return fail(nullptr, FVHD_ERR_INVALID, "null argument");
+    if (cfg->image_size < 64 || cfg->image_size % 64) return fail(nullptr, FVHD_ERR_INVALID, "image_size must be a positive multiple of 64 (got %d)", cfg->image_size);
+    if (cfg->projector_hidden < 0 || cfg->projector_hidden % 8) return fail(nullptr, FVHD_ERR_INVALID, "projector_hidden must be a multiple of 8 (got %d)", cfg->projector_hidden);
+    if (cfg->projector_hidden > 0 && cfg->projector_depth != 1 && cfg->projector_depth != 2)
+        return fail(nullptr, FVHD_ERR_INVALID, "projector_depth must be 1 or 2 (mlp{N}x_gelu), got %d", cfg->projector_depth);
+    if (cfg->max_batch < 1) return fail(nullptr, FVHD_ERR_INVALID, "max_batch must be >= 1");
+    fvhd_handle h = new fvhd_handle_s();
+    h->cfg = *cfg;
+    h->R = cfg->image_size;
+    h->ntok = (cfg->image_size / FVHD_PATCH) * (cfg->image_size / FVHD_PATCH);
+    build_arch(h);
+    *out = h;
+    return FVHD_OK;
+}
+
+int fvhd_destroy(fvhd_handle h) {
+    if (h) {
+        if (h->stage_in) cudaFree(h->stage_in);
+        if (h->stage_out) cudaFree(h->stage_out);
+    }
+    delete h;
+    return FVHD_OK;
+}
+
+int fvhd_num_weights(fvhd_handle h) { return h ? (int)h->specs.size() : FVHD_ERR_INVALID; }
+
+int fvhd_weight_spec(fvhd_handle h, int i, const char** name, int* dtype, int64_t* numel) {
+    if (!h || i < 0 || i >= (int)h->specs.size()) return FVHD_ERR_INVALID;
+    if (name) *name = h->specs[i].name.c_str();
+    if (dtype) *dtype = h->specs[i].dtype;
+    if (numel) *numel = h->specs[i].numel;
+    return FVHD_OK;
+}
+
+int fvhd_load_weights(fvhd_handle h, const fvhd_tensor* table, int n) {
+    if (!h || !table) return FVHD_ERR_INVALID;
+    std::map<std::string, const fvhd_tensor*> got;
+    for (int i = 0; i < n; ++i) {
+        if (!table[i].name) return fail(h, FVHD_ERR_WEIGHTS, "weight table entry %d has no name", i);
+        got[table[i].name] = &table[i];
+    }
+    std::map<std::string, const void*> wp;
+    for (const WeightSpec& s : h->specs) {
+        auto it = got.find(s.name);
+        if (it == got.end()) return fail(h, FVHD_ERR_WEIGHTS, "missing weight tensor '%s'", s.name.c_str());
+        const fvhd_tensor* t = it->second;
+        if (t->dtype != s.dtype || t->numel != s.numel)
+            return fail(h, FVHD_ERR_WEIGHTS, "weight '%s': expected dtype %d numel %lld, got dtype %d numel %lld", s.name.c_str(), s.dtype,
+                        (long long)s.numel, t->dtype, (long long)t->numel);
+        if (!t->data || ((uintptr_t)t->data & 15)) return fail(h, FVHD_ERR_WEIGHTS, "weight '%s': device pointer must be non-null and 16-B aligned", s.name.c_str());
+        wp[s.name] = t->data;
+    }
+    h->wptr.swap(wp);
+    h->plans.clear();
+    h->loaded = true;
+    return FVHD_OK;
+}
+
+size_t fvhd_workspace_bytes(fvhd_handle h, int batch) {
+    if (!h || batch < 1) return 0;
+    const int bc = batch < h->cfg.max_batch ? batch : h->cfg.max_batch;
+    return workspace_bytes(h, bc);
+}
+
+int fvhd_set_workspace(fvhd_handle h, void* dptr, size_t bytes) {
+    if (!h) return FVHD_ERR_INVALID;
+    h->ws = dptr;
+    h->ws_bytes = bytes;
+    h->plans.clear();
+    return FVHD_OK;
+}
+
+int fvhd_num_tokens(fvhd_handle h) { return h ? h->ntok : FVHD_ERR_INVALID; }
+int fvhd_out_dim(fvhd_handle h) { return h ? (h->cfg.projector_hidden > 0 ? h->cfg.projector_hidden : FVHD_EMBED_DIM) : FVHD_ERR_INVALID; }
+int fvhd_num_units(fvhd_handle h) { return h ? (int)h->units.size() : FVHD_ERR_INVALID; }
+
+int fvhd_unit_info(fvhd_handle h, int u, const char** name, int64_t* in_elems, int64_t* out_elems, int* out_h, int* out_w, int* out_c,
+                   double* flops, double* min_bytes) {
+    if (!h || u < 0 || u >= (int)h->units.size()) return FVHD_ERR_INVALID;
+    const UnitDesc& d = h->units[u];
+    if (name) *name = d.name.c_str();
+    if (in_elems) *in_elems = d.in_elems;
+    if (out_elems) *out_elems = d.out_elems;
+    if (out_h) *out_h = d.hout;
+    if (out_w) *out_w = d.wout;
+    if (out_c) *out_c = d.cout;
+    if (flops) *flops = d.flops;
+    if (min_bytes) *min_bytes = d.min_bytes;
+    return FVHD_OK;
+}
+
+int fvhd_launches_per_forward(fvhd_handle h, int batch) {
+    if (!h) return FVHD_ERR_INVALID;
+    // steps per pass, + 2 for the three-kernel SE step, x number of passes
+    int steps = 0;
+    for (const UnitDesc& u : h->units) {
+        switch (u.kind) {
+        case 0: steps += 2; break;
+        case 1: steps += 3; break;
+        case 2: steps += 2; break;
+        case 3: steps += 1; break;
+        case 4: steps += 7; break;
+        case 5: steps += 4; break;   // dw + pool + reduce + expand
+        case 6: steps += h->cfg.projector_depth; break;
+        }
+    }
+    const int passes = (batch + h->cfg.max_batch - 1) / h->cfg.max_batch;
+    return steps * passes;
+}
+
+int fvhd_forward(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch, void* tokens, void* projected) {
+    int rc = check_ready(h, batch);
+    if (rc != FVHD_OK) return rc;
+    if (!images) return fail(h, FVHD_ERR_INVALID, "images is null");
+    if (img_dtype < FVHD_F32 || img_dtype > FVHD_BF16) return fail(h, FVHD_ERR_INVALID, "unsupported image dtype %d", img_dtype);
+    const bool has_proj = h->cfg.projector_hidden > 0;
+    if (projected && !has_proj) return fail(h, FVHD_ERR_INVALID, "projected output requested but the plan has no projector");
+    if (!tokens && !projected) return fail(h, FVHD_ERR_INVALID, "both outputs are null");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t img_stride = (size_t)3 * h->R * h->R * dtype_size(img_dtype);
+    const size_t tok_stride = (size_t)h->ntok * FVHD_EMBED_DIM * 2;
+    const size_t prj_stride = (size_t)h->ntok * h->cfg.projector_hidden * 2;
+    const int nunits = (int)h->units.size();
+    const int tok_unit = has_proj ? nunits - 2 : nunits - 1;
+    for (int b0 = 0; b0 < batch; b0 += h->cfg.max_batch) {
+        const int bc = (batch - b0) < h->cfg.max_batch ? (batch - b0) : h->cfg.max_batch;
+        Plan* pl;
+        if ((rc = get_plan(h, bc, &pl)) != FVHD_OK) return rc;
+        RunCtx ctx;
+        ctx.images = reinterpret_cast<const uint8_t*>(images) + (size_t)b0 * img_stride;
+        ctx.img_dtype = img_dtype;
+        uint8_t* tok_dst = tokens ? reinterpret_cast<uint8_t*>(tokens) + (size_t)b0 * tok_stride : nullptr;
+        uint8_t* prj_dst = projected ? reinterpret_cast<uint8_t*>(projected) + (size_t)b0 * prj_stride : nullptr;
+        if (has_proj) {
+            // tokens stay in the workspace (the projector's TMA map points there); copy out if requested
+            const int last_unit = projected ? nunits - 1 : nunits - 2;
+            ctx.final_out = prj_dst;
+            if ((rc = run_steps(h, *pl, 0, pl->unit_steps[last_unit].second, st, ctx)) != FVHD_OK) return rc;
+            if (tok_dst) CUDA_TRY(h, cudaMemcpyAsync(tok_dst, pl->unit_out[tok_unit], (size_t)bc * tok_stride, cudaMemcpyDeviceToDevice, st));
+        } else {
+            ctx.final_out = tok_dst;
+            if ((rc = run_steps(h, *pl, 0, (int)pl->steps.size(), st, ctx)) != FVHD_OK) return rc;
+        }
+    }
+    return FVHD_OK;
+}
+
+int fvhd_encode_images_host(fvhd_handle h, void* stream, const void* host_images, int img_dtype, int batch, void* host_out) {
+    int rc = check_ready(h, batch);
+    if (rc != FVHD_OK) return rc;
+    if (!host_images || !host_out) return fail(h, FVHD_ERR_INVALID, "null host buffer");
+    if (batch > h->cfg.max_batch) return fail(h, FVHD_ERR_INVALID, "fvhd_encode_images_host: batch %d > max_batch %d", batch, h->cfg.max_batch);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t img_bytes = (size_t)batch * 3 * h->R * h->R * dtype_size(img_dtype);
+    const size_t out_bytes = (size_t)batch * h->ntok * fvhd_out_dim(h) * 2;
+    // device staging owned by the handle (grown on demand)
+    if (h->stage_in_bytes < img_bytes) {
+        if (h->stage_in) cudaFree(h->stage_in);
+        h->stage_in = nullptr; h->stage_in_bytes = 0;
+        CUDA_TRY(h, cudaMalloc(&h->stage_in, img_bytes));
+        h->stage_in_bytes = img_bytes;
+    }
+    if (h->stage_out_bytes < out_bytes) {
+        if (h->stage_out) cudaFree(h->stage_out);
+        h->stage_out = nullptr; h->stage_out_bytes = 0;
+        CUDA_TRY(h, cudaMalloc(&h->stage_out, out_bytes));
+        h->stage_out_bytes = out_bytes;
+    }
+    void* stage_in = h->stage_in;
+    void* stage_out = h->stage_out;
+    CUDA_TRY(h, cudaMemcpyAsync(stage_in, host_images, img_bytes, cudaMemcpyHostToDevice, st));
+    const bool has_proj = h->cfg.projector_hidden > 0;
+    rc = fvhd_forward(h, stream, stage_in, img_dtype, batch, has_proj ? nullptr : stage_out, has_proj ? stage_out : nullptr);
+    if (rc != FVHD_OK) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(host_out, stage_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    return FVHD_OK;
+}
+
+int fvhd_run_units(fvhd_handle h, void* stream, int first, int last, const void* in, int img_dtype, int batch, void* out) {
+    int rc = check_ready(h, batch);
+    if (rc != FVHD_OK) return rc;
+    const int nunits = (int)h->units.size();
+    if (first < 0 || last >= nunits || first > last) return fail(h, FVHD_ERR_INVALID, "bad unit range [%d, %d]", first, last);
+    if (batch > h->cfg.max_batch) return fail(h, FVHD_ERR_INVALID, "fvhd_run_units: batch %d > max_batch %d", batch, h->cfg.max_batch);
+    if (!in || !out) return fail(h, FVHD_ERR_INVALID, "null buffer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Plan* pl;
+    if ((rc = get_plan(h, batch, &pl)) != FVHD_OK) return rc;
+    RunCtx ctx;
+    ctx.images = in;
+    ctx.img_dtype = img_dtype;
+    ctx.final_out = nullptr;
+    if (first > 0)
+        CUDA_TRY(h, cudaMemcpyAsync(pl->unit_in[first], in, (size_t)batch * h->units[first].in_elems * 2, cudaMemcpyDeviceToDevice, st));
+    const size_t out_bytes = (size_t)batch * h->units[last].out_elems * 2;
+    if (last == nunits - 1) {
+        ctx.final_out = out;      // the last unit of the plan writes straight to the caller's buffer
+        return run_steps(h, *pl, pl->unit_steps[first].first, pl->unit_steps[last].second, st, ctx);
+    }
+    if ((rc = run_steps(h, *pl, pl->unit_steps[first].first, pl->unit_steps[last].second, st, ctx)) != FVHD_OK) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(out, pl->unit_out[last], out_bytes, cudaMemcpyDeviceToDevice, st));
+    return FVHD_OK;
+}
+
+int fvhd_profile_units(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch, float* ms, int n_ms) {
+    int rc = check_ready(h, batch);
+    if (rc != FVHD_OK) return rc;
+    const int nunits = (int)h->units.size();
+    if (!ms || n_ms < nunits) return fail(h, FVHD_ERR_INVALID, "ms buffer too small (%d < %d)", n_ms, nunits);
+    if (batch > h->cfg.max_batch) return fail(h, FVHD_ERR_INVALID, "fvhd_profile_units: batch %d > max_batch %d", batch, h->cfg.max_batch);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Plan* pl;
+    if ((rc = get_plan(h, batch, &pl)) != FVHD_OK) return rc;
+    std::vector<cudaEvent_t> ev(nunits + 1);
+    for (auto& e : ev) CUDA_TRY(h, cudaEventCreate(&e));
+    RunCtx ctx;
+    ctx.images = images;
+    ctx.img_dtype = img_dtype;
+    ctx.final_out = pl->unit_out[nunits - 1];   // keep the final result inside the workspace
+    CUDA_TRY(h, cudaEventRecord(ev[0], st));
+    for (int u = 0; u < nunits; ++u) {
+        if ((rc = run_steps(h, *pl, pl->unit_steps[u].first, pl->unit_steps[u].second, st, ctx)) != FVHD_OK) return rc;
+        CUDA_TRY(h, cudaEventRecord(ev[u + 1], st));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    for (int u = 0; u < nunits; ++u) CUDA_TRY(h, cudaEventElapsedTime(&ms[u], ev[u], ev[u + 1]));
+    for (auto& e : ev) cudaEventDestroy(e);
+    return FVHD_OK;
+}
+
+int fvhd_num_steps(fvhd_handle h, int batch) {
+    int rc = check_ready(h, batch);
+    if (rc != FVHD_OK) return rc;
+    Plan* pl;
+    if ((rc = get_plan(h, batch, &pl)) != FVHD_OK) return rc;
+    return (int)pl->steps.size();
+}
+
+int fvhd_step_info(fvhd_handle h, int batch, int i, const char** kernel, int* unit, double* flops, double* bytes) {
+    int rc = check_ready(h, batch);
+    if (rc != FVHD_OK) return rc;
+    Plan* pl;
+    if ((rc = get_plan(h, batch, &pl)) != FVHD_OK) return rc;
+    if (i < 0 || i >= (int)pl->info.size()) return fail(h, FVHD_ERR_INVALID, "step %d out of range", i);
+    if (kernel) *kernel = pl->info[i].kernel;
+    if (unit) *unit = pl->info[i].unit;
+    if (flops) *flops = pl->info[i].flops;
+    if (bytes) *bytes = pl->info[i].bytes;
+    return FVHD_OK;
+}
+
+int fvhd_profile_steps(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch, float* ms, int n_ms) {
+    int rc = check_ready(h, batch);
+    if (rc != FVHD_OK) return rc;
+    if (batch > h->cfg.max_batch) return fail(h, FVHD_ERR_INVALID, "fvhd_profile_steps: batch %d > max_batch %d", batch, h->cfg.max_batch);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Plan* pl;
+    if ((rc = get_plan(h, batch, &pl)) != FVHD_OK) return rc;
+    const int n = (int)pl->steps.size();
+    if (!ms || n_ms < n) return fail(h, FVHD_ERR_INVALID, "ms buffer too small (%d < %d)", n_ms, n);
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) CUDA_TRY(h, cudaEventCreate(&e));
+    RunCtx ctx;
+    ctx.images = images;
+    ctx.img_dtype = img_dtype;
+    ctx.final_out = pl->unit_out[h->units.size() - 1];
+    CUDA_TRY(h, cudaEventRecord(ev[0], st));
+    for (int i = 0; i < n; ++i) {
+        if ((rc = run_steps(h, *pl, i, i + 1, st, ctx)) != FVHD_OK) return rc;
+        CUDA_TRY(h, cudaEventRecord(ev[i + 1], st));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    for (int i = 0; i < n; ++i) CUDA_TRY(h, cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    for (auto& e : ev) cudaEventDestroy(e);
+    return FVHD_OK;
+}
+
+int fvhd_gemm(fvhd_handle h, void* stream, const void* A, const void* W, const void* bias, const void* residual, void* D, int M, int N, int K, int act) {
+    if (!h) return FVHD_ERR_INVALID;
+    int rc = ensure_cuda(h);
+    if (rc != FVHD_OK) return rc;
+    Step s;
+    if ((rc = make_gemm_step(h, &s, (const bf16*)A, K, (const bf16*)W, (const float*)bias, (const bf16*)residual, N, (bf16*)D, N, M, N, K, act)) != FVHD_OK) return rc;
+    RunCtx ctx{};
+    cudaError_t e = s(reinterpret_cast<cudaStream_t>(stream), ctx);
+    if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "gemm launch failed: %s", cudaGetErrorString(e));
+    return FVHD_OK;
+}
+
+}  // extern "C"

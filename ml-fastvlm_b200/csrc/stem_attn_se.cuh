@@ -1,0 +1,383 @@
+// Stem, channel LayerNorm, MHSA core and conv_exp squeeze-excite kernels (NHWC bf16 activations).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "ptx.cuh"
+
+namespace fvhd {
+
+// ====================================================================== stem
+// convolutional_stem blocks 0 and 1 fused (mci.py:567-590): NCHW image (fp32/fp16/bf16) ->
+// conv3x3 s2 (3->96) + GELU -> dw3x3 s2 + GELU -> NHWC bf16 [B, R/4, R/4, 96].
+// The R/2 x R/2 x 96 intermediate (50 MB / image at R=1024) never reaches HBM: a CTA computes the
+// 17x17 conv0 patch its 8x8 output tile needs into shared memory.  Block 2 (1x1 + GELU) is a GEMM.
+constexpr int STEM_C = 96;
+constexpr int STEM_TO = 8;                       // output tile (at R/4)
+constexpr int STEM_MID = 2 * STEM_TO + 1;        // 17: conv0 patch edge
+constexpr int STEM_IN = 2 * STEM_MID + 1;        // 35: input patch edge
+constexpr int STEM_INP = STEM_IN + 1;            // 36: padded pitch
+constexpr int STEM_MIDP = STEM_C / 2 + 1;        // 49 words per conv0 pixel (bf16 pairs, +1 pad)
+constexpr int STEM_THREADS = 256;
+constexpr size_t STEM_SMEM = (size_t)(3 * STEM_IN * STEM_INP + STEM_MID * STEM_MID * STEM_MIDP + 27 * STEM_C + 9 * STEM_C + 2 * STEM_C) * 4;
+
+template <typename T> __device__ __forceinline__ float img_ld(const T* p);
+template <> __device__ __forceinline__ float img_ld<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float img_ld<__half>(const __half* p) { return __half2float(*p); }
+template <> __device__ __forceinline__ float img_ld<bf16>(const bf16* p) { return __bfloat162float(*p); }
+
+template <typename T>
+__global__ void __launch_bounds__(STEM_THREADS)
+stem_kernel(const T* __restrict__ img, bf16* __restrict__ out, const float* __restrict__ w0 /*[27][96], k=(ci*3+ky)*3+kx*/,
+            const float* __restrict__ b0, const float* __restrict__ w1 /*[9][96]*/, const float* __restrict__ b1, int R, int tiles_x) {
+    extern __shared__ __align__(16) float stem_smem[];
+    float* sin = stem_smem;                                              // [3][35][36]
+    uint32_t* s1 = reinterpret_cast<uint32_t*>(sin + 3 * STEM_IN * STEM_INP);   // [289][49]
+    float* w0s = reinterpret_cast<float*>(s1 + STEM_MID * STEM_MID * STEM_MIDP);
+    float* w1s = w0s + 27 * STEM_C;
+    float* b0s = w1s + 9 * STEM_C;
+    float* b1s = b0s + STEM_C;
+
+    const int b = blockIdx.z;
+    const int ty0 = (blockIdx.x / tiles_x) * STEM_TO, tx0 = (blockIdx.x % tiles_x) * STEM_TO;
+    const int R2 = R / 2, R4 = R / 4;
+    const int iy0 = 4 * ty0 - 3, ix0 = 4 * tx0 - 3;     // input patch origin
+    const int cy0 = 2 * ty0 - 1, cx0 = 2 * tx0 - 1;     // conv0 patch origin
+
+    for (int i = threadIdx.x; i < 27 * STEM_C; i += STEM_THREADS) w0s[i] = __ldg(w0 + i);
+    for (int i = threadIdx.x; i < 9 * STEM_C; i += STEM_THREADS) w1s[i] = __ldg(w1 + i);
+    if (threadIdx.x < STEM_C) { b0s[threadIdx.x] = __ldg(b0 + threadIdx.x); b1s[threadIdx.x] = __ldg(b1 + threadIdx.x); }
+    for (int i = threadIdx.x; i < 3 * STEM_IN * STEM_IN; i += STEM_THREADS) {
+        const int ci = i / (STEM_IN * STEM_IN);
+        const int rem = i - ci * STEM_IN * STEM_IN;
+        const int yy = rem / STEM_IN, xx = rem - yy * STEM_IN;
+        const int gy = iy0 + yy, gx = ix0 + xx;
+        float v = 0.f;
+        if (gy >= 0 && gy < R && gx >= 0 && gx < R) v = img_ld<T>(img + (((size_t)b * 3 + ci) * R + gy) * R + gx);
+        sin[(ci * STEM_IN + yy) * STEM_INP + xx] = v;
+    }
+    __syncthreads();
+
+    // phase 1: conv0 3x3 s2 + GELU on the 17x17 patch; item = (24-channel group, pixel)
+    for (int it = threadIdx.x; it < 4 * STEM_MID * STEM_MID; it += STEM_THREADS) {
+        const int g = it / (STEM_MID * STEM_MID);
+        const int p = it - g * STEM_MID * STEM_MID;
+        const int py = p / STEM_MID, px = p - py * STEM_MID;
+        const int cy = cy0 + py, cx = cx0 + px;
+        uint32_t* dst = s1 + p * STEM_MIDP + g * 12;
+        if (cy < 0 || cy >= R2 || cx < 0 || cx >= R2) {     // zero padding of the depthwise conv
+#pragma unroll
+            for (int j = 0; j < 12; ++j) dst[j] = 0u;
+            continue;
+        }
+        float acc[24];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) acc[j] = b0s[g * 24 + j];
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float xv = sin[(ci * STEM_IN + 2 * py + ky) * STEM_INP + 2 * px + kx];
+                    const float4* wp = reinterpret_cast<const float4*>(w0s + ((ci * 3 + ky) * 3 + kx) * STEM_C + g * 24);
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        const float4 w = wp[j];
+                        acc[4 * j + 0] = fmaf(xv, w.x, acc[4 * j + 0]);
+                        acc[4 * j + 1] = fmaf(xv, w.y, acc[4 * j + 1]);
+                        acc[4 * j + 2] = fmaf(xv, w.z, acc[4 * j + 2]);
+                        acc[4 * j + 3] = fmaf(xv, w.w, acc[4 * j + 3]);
+                    }
+                }
+#pragma unroll
+        for (int j = 0; j < 12; ++j) dst[j] = pack_bf16x2(gelu_erf(acc[2 * j]), gelu_erf(acc[2 * j + 1]));
+    }
+    __syncthreads();
+
+    // phase 2: depthwise 3x3 s2 + GELU; item = (output pixel, channel pair)
+    for (int it = threadIdx.x; it < STEM_TO * STEM_TO * (STEM_C / 2); it += STEM_THREADS) {
+        const int op = it / (STEM_C / 2);
+        const int cp = it - op * (STEM_C / 2);
+        const int oy = op / STEM_TO, ox = op - oy * STEM_TO;
+        float a0 = b1s[2 * cp], a1 = b1s[2 * cp + 1];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float2 v = unpack_bf16x2(s1[((2 * oy + ky) * STEM_MID + 2 * ox + kx) * STEM_MIDP + cp]);
+                const float2 w = *reinterpret_cast<const float2*>(w1s + (ky * 3 + kx) * STEM_C + 2 * cp);
+                a0 = fmaf(v.x, w.x, a0);
+                a1 = fmaf(v.y, w.y, a1);
+            }
+        const int gy = ty0 + oy, gx = tx0 + ox;
+        if (gy < R4 && gx < R4)
+            *reinterpret_cast<uint32_t*>(out + (((size_t)b * R4 + gy) * R4 + gx) * STEM_C + 2 * cp) = pack_bf16x2(gelu_erf(a0), gelu_erf(a1));
+    }
+}
+
+// ====================================================================== LayerNormChannel
+// mci.py:617-623: per-pixel LayerNorm over channels (eps 1e-5), fp32 statistics, two-pass in registers.
+// One warp per pixel row of the [M, C] activation matrix.  NV = C / 256.
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_channel_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, int M, float eps) {
+    constexpr int C = NV * 256;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    float v[NV * 8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (size_t)row * C + (i * 32 + lane) * 8));
+        const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+        v[i * 8 + 0] = f0.x; v[i * 8 + 1] = f0.y; v[i * 8 + 2] = f1.x; v[i * 8 + 3] = f1.y;
+        v[i * 8 + 4] = f2.x; v[i * 8 + 5] = f2.y; v[i * 8 + 6] = f3.x; v[i * 8 + 7] = f3.y;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += v[i * 8 + j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.0f / C);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV * 8; ++i) { const float d = v[i] - mean; sq = fmaf(d, d, sq); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.0f / C) + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+        uint4 o;
+        o.x = pack_bf16x2((v[i * 8 + 0] - mean) * rstd * g0.x + b0.x, (v[i * 8 + 1] - mean) * rstd * g0.y + b0.y);
+        o.y = pack_bf16x2((v[i * 8 + 2] - mean) * rstd * g0.z + b0.z, (v[i * 8 + 3] - mean) * rstd * g0.w + b0.w);
+        o.z = pack_bf16x2((v[i * 8 + 4] - mean) * rstd * g1.x + b1.x, (v[i * 8 + 5] - mean) * rstd * g1.y + b1.y);
+        o.w = pack_bf16x2((v[i * 8 + 6] - mean) * rstd * g1.z + b1.z, (v[i * 8 + 7] - mean) * rstd * g1.w + b1.w);
+        *reinterpret_cast<uint4*>(y + (size_t)row * C + c) = o;
+    }
+}
+
+// ====================================================================== MHSA core
+// softmax((q * 32^-1/2) k^T) v per head of dim 32 (mci.py:675-679), flash-style: the [N,N] score
+// matrix the reference materialises never exists; scores live in mma.sync accumulators, the online
+// softmax runs in fp32 with exp2.  qkv is the row-major [B*N, 3C] output of the qkv GEMM
+// (q | k | v, each split into heads of 32 -- the reshape(B,N,3,h,32) of mci.py:669-672).
+// grid (ceil(N/64), heads, B), 128 threads: a warp owns 16 query rows; K/V stream through a
+// double-buffered cp.async ring in chunks of 64 keys.
+constexpr int ATT_KC = 64;
+constexpr int ATT_PITCH = 40;      // bf16 per smem row (32 + 8 pad): conflict-free LDS.32 / ldmatrix
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPEND> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
+
+__global__ void __launch_bounds__(128)
+attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int N, int C, float scale_log2e) {
+    __shared__ __align__(16) bf16 Ks[2][ATT_KC * ATT_PITCH];
+    __shared__ __align__(16) bf16 Vs[2][ATT_KC * ATT_PITCH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int head = blockIdx.y, b = blockIdx.z;
+    const size_t ld = (size_t)3 * C;
+    const bf16* base = qkv + (size_t)b * N * ld + head * 32;
+    const int q0 = blockIdx.x * 64 + warp * 16;
+
+    auto load_chunk = [&](int chunk, int buf) {
+        // 64 keys x (K 64 B + V 64 B) = 512 x 16-B pieces, 4 per thread
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int piece = threadIdx.x + i * 128;
+            const int which = piece >> 8;            // 0 = K, 1 = V
+            const int key = (piece & 255) >> 2;
+            const int part = piece & 3;
+            const int gk = chunk * ATT_KC + key;
+            bf16* dst = (which ? Vs[buf] : Ks[buf]) + key * ATT_PITCH + part * 8;
+            if (gk < N) cp_async16(dst, base + (size_t)gk * ld + (which + 1) * C + part * 8);
+            else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+        }
+        cp_async_commit();
+    };
+
+    uint32_t qa[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        const int r0 = q0 + g, r1 = q0 + g + 8;
+        const int c = ks * 16 + t * 2;
+        qa[ks][0] = r0 < N ? *reinterpret_cast<const uint32_t*>(base + (size_t)r0 * ld + c) : 0u;
+        qa[ks][1] = r1 < N ? *reinterpret_cast<const uint32_t*>(base + (size_t)r1 * ld + c) : 0u;
+        qa[ks][2] = r0 < N ? *reinterpret_cast<const uint32_t*>(base + (size_t)r0 * ld + c + 8) : 0u;
+        qa[ks][3] = r1 < N ? *reinterpret_cast<const uint32_t*>(base + (size_t)r1 * ld + c + 8) : 0u;
+    }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float o[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+
+    const int nchunks = (N + ATT_KC - 1) / ATT_KC;
+    load_chunk(0, 0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int buf = ch & 1;
+        if (ch + 1 < nchunks) { load_chunk(ch + 1, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        const bf16* Kb = Ks[buf];
+        const bf16* Vb = Vs[buf];
+
+        float s[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const bf16* kp = Kb + (j * 8 + g) * ATT_PITCH + ks * 16 + t * 2;
+                mma_bf16_16816(s[j], qa[ks], *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 8));
+            }
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int key = ch * ATT_KC + j * 8 + t * 2;
+            s[j][0] = key < N ? s[j][0] * scale_log2e : -INFINITY;
+            s[j][1] = key + 1 < N ? s[j][1] * scale_log2e : -INFINITY;
+            s[j][2] = key < N ? s[j][2] * scale_log2e : -INFINITY;
+            s[j][3] = key + 1 < N ? s[j][3] * scale_log2e : -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float a0 = exp2f(m0 - mn0), a1 = exp2f(m1 - mn1);
+        m0 = mn0; m1 = mn1;
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s[j][0] = exp2f(s[j][0] - mn0); s[j][1] = exp2f(s[j][1] - mn0);
+            s[j][2] = exp2f(s[j][2] - mn1); s[j][3] = exp2f(s[j][3] - mn1);
+            rs0 += s[j][0] + s[j][1];
+            rs1 += s[j][2] + s[j][3];
+        }
+        l0 = l0 * a0 + rs0;
+        l1 = l1 * a1 + rs1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { o[i][0] *= a0; o[i][1] *= a0; o[i][2] *= a1; o[i][3] *= a1; }
+
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {          // 16 keys per step
+            uint32_t pa[4];
+            pa[0] = pack_bf16x2(s[2 * k2][0], s[2 * k2][1]);
+            pa[1] = pack_bf16x2(s[2 * k2][2], s[2 * k2][3]);
+            pa[2] = pack_bf16x2(s[2 * k2 + 1][0], s[2 * k2 + 1][1]);
+            pa[3] = pack_bf16x2(s[2 * k2 + 1][2], s[2 * k2 + 1][3]);
+#pragma unroll
+            for (int nt = 0; nt < 4; nt += 2) {   // two 8-wide dim tiles per ldmatrix.x4
+                const int mi = lane >> 3, r = lane & 7;
+                const int key = k2 * 16 + (mi & 1) * 8 + r;
+                const int dim0 = (nt + (mi >> 1)) * 8;
+                uint32_t vb[4];
+                ldmatrix_x4_trans(vb, Vb + key * ATT_PITCH + dim0);
+                mma_bf16_16816(o[nt], pa, vb[0], vb[1]);
+                mma_bf16_16816(o[nt + 1], pa, vb[2], vb[3]);
+            }
+        }
+        __syncthreads();
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    const int r0 = q0 + g, r1 = q0 + g + 8;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const int c = head * 32 + nt * 8 + t * 2;
+        if (r0 < N) *reinterpret_cast<uint32_t*>(out + ((size_t)b * N + r0) * C + c) = pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
+        if (r1 < N) *reinterpret_cast<uint32_t*>(out + ((size_t)b * N + r1) * C + c) = pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
+    }
+}
+
+// ====================================================================== conv_exp squeeze-excite
+// SEBlock (mci.py:72-81) on the dw3x3 output c [B, HW, C]:  s = sigmoid(We relu(Wr mean_hw(c) + br) + be),
+// tokens = GELU(c * s) (order act(se(conv(x))), mci.py:198), emitted directly as [B, HW, 3072].
+// grid (C/64, B): per-channel mean over the HW pixels of one image.
+__global__ void __launch_bounds__(256)
+se_pool_kernel(const bf16* __restrict__ c, float* __restrict__ pooled, int HW, int C) {
+    __shared__ float red[8][64];
+    const int b = blockIdx.y, c0 = blockIdx.x * 64;
+    const int cp = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    float a0 = 0.f, a1 = 0.f;
+    for (int p = sl; p < HW; p += 8) {
+        const float2 v = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(c + ((size_t)b * HW + p) * C + c0 + 2 * cp)));
+        a0 += v.x; a1 += v.y;
+    }
+    red[sl][2 * cp] = a0; red[sl][2 * cp + 1] = a1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+        pooled[(size_t)b * C + c0 + threadIdx.x] = s / (float)HW;
+    }
+}
+// grid (RD/8, B): warp per reduced channel.
+__global__ void __launch_bounds__(256)
+se_reduce_kernel(const float* __restrict__ pooled, const bf16* __restrict__ wr /*[RD][C]*/, const float* __restrict__ br,
+                 float* __restrict__ r, int C, int RD) {
+    const int b = blockIdx.y, j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= RD) return;
+    float a = 0.f;
+    for (int c = lane * 8; c < C; c += 256) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(wr + (size_t)j * C + c));
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(pooled + (size_t)b * C + c));
+        const float4 p1 = __ldg(reinterpret_cast<const float4*>(pooled + (size_t)b * C + c + 4));
+        const float2 w0 = unpack_bf16x2(u.x), w1 = unpack_bf16x2(u.y), w2 = unpack_bf16x2(u.z), w3 = unpack_bf16x2(u.w);
+        a += w0.x * p0.x + w0.y * p0.y + w1.x * p0.z + w1.y * p0.w + w2.x * p1.x + w2.y * p1.y + w3.x * p1.z + w3.y * p1.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) r[(size_t)b * RD + j] = fmaxf(a + __ldg(br + j), 0.f);
+}
+// grid (C/128, B): expand + sigmoid for a 128-channel slice, then scale + GELU all HW pixels of it.
+__global__ void __launch_bounds__(256)
+se_expand_scale_gelu_kernel(const bf16* __restrict__ c, const float* __restrict__ r, const bf16* __restrict__ we /*[C][RD]*/,
+                            const float* __restrict__ be, bf16* __restrict__ tokens, int HW, int C, int RD) {
+    __shared__ float rs[256];
+    __shared__ float ss[128];
+    const int b = blockIdx.y, c0 = blockIdx.x * 128;
+    for (int i = threadIdx.x; i < RD; i += 256) rs[i] = r[(size_t)b * RD + i];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int ch = c0 + threadIdx.x;
+        float a = __ldg(be + ch);
+        for (int j = 0; j < RD; j += 8) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(we + (size_t)ch * RD + j));
+            const float2 w0 = unpack_bf16x2(u.x), w1 = unpack_bf16x2(u.y), w2 = unpack_bf16x2(u.z), w3 = unpack_bf16x2(u.w);
+            a += w0.x * rs[j] + w0.y * rs[j + 1] + w1.x * rs[j + 2] + w1.y * rs[j + 3] + w2.x * rs[j + 4] + w2.y * rs[j + 5] + w3.x * rs[j + 6] + w3.y * rs[j + 7];
+        }
+        ss[threadIdx.x] = 1.0f / (1.0f + __expf(-a));
+    }
+    __syncthreads();
+    const int cp = threadIdx.x & 63;
+    const float s0 = ss[2 * cp], s1 = ss[2 * cp + 1];
+    for (int p = threadIdx.x >> 6; p < HW; p += 4) {
+        const size_t off = ((size_t)b * HW + p) * C + c0 + 2 * cp;
+        const float2 v = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(c + off)));
+        *reinterpret_cast<uint32_t*>(tokens + off) = pack_bf16x2(gelu_erf(v.x * s0), gelu_erf(v.y * s1));
+    }
+}
+
+}  // namespace fvhd

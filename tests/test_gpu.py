@@ -1,0 +1,237 @@
+"""GPU parity tests (-m gpu): the CUDA path through the C ABI vs the oracle, the golden vectors of the
+unmodified reference, and size-independent properties at the bench size.
+
+Tolerances (bf16 activations + bf16 GEMM weights, fp32 accumulation, vs the fp32 oracle):
+  * a single unit fed the oracle's own input ........ rel-L2 <= 1.5e-2
+  * whole tower / encode_images (51 units chained) .. rel-L2 <= 3e-2
+    (the reference's own bf16-vs-fp32 run differs by 7.6e-3; bf16 weight rounding alone gives ~7e-3)
+  * token count / shapes ............................ exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ml_fastvlm_b200 as pkg
+from oracle import fastvithd_oracle as orc
+from oracle import fixture as fx
+
+pytestmark = pytest.mark.gpu
+
+UNIT_TOL = 1.5e-2
+E2E_TOL = 3e-2
+
+
+def rel_l2(a, b):
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def packed(tower_sd, proj_sd):
+    pk = pkg.pack_tower(tower_sd)
+    pk.update(pkg.pack_projector(proj_sd))
+    return pk
+
+
+@pytest.fixture(scope="module")
+def eng256(packed, dev):
+    return pkg.Engine(256, 896, 2, 2).load(packed, dev)
+
+
+@pytest.fixture(scope="module")
+def oracle256(tower_sd, proj_sd):
+    col = {}
+    out = orc.encode_images(fx.synthetic_images(1, 256), tower_sd, proj_sd, col)
+    return out, col
+
+
+# ------------------------------------------------------------------ tcgen05 GEMM
+@pytest.mark.parametrize("M,N,K,act,use_bias,use_res", [
+    (128, 128, 64, 0, False, False),       # one tile, one k-block
+    (128, 128, 512, 0, False, False),      # ring wraps (8 k-blocks, 3 stages)
+    (1000, 96, 96, 1, True, False),        # ragged M, BN=96, K not a multiple of 64 (TMA zero fill)
+    (65536, 96, 96, 1, True, False),       # stem 1x1 at R=1024
+    (4096, 1536, 384, 1, True, False),     # stage-2 fc1
+    (4096, 384, 1536, 0, True, True),      # stage-2 fc2 + residual
+    (16, 896, 3072, 1, True, False),       # projector layer 0 at R=256 (M << tile)
+    (300, 2304, 768, 0, False, False),     # qkv, no bias
+    (512, 200, 256, 0, True, False),       # N % 32 != 0 (column tail)
+    (1, 3584, 3584, 0, True, False),       # single row
+])
+def test_gemm_against_fp32(dev, M, N, K, act, use_bias, use_res):
+    eng = pkg.Engine(64, 0, 2, 1)
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16).to(dev)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(dev)
+    b = torch.randn(N, generator=g).to(dev) if use_bias else None
+    r = torch.randn(M, N, generator=g).to(torch.bfloat16).to(dev) if use_res else None
+    D = eng.gemm(A, W, b, r, act)
+    ref = A.float() @ W.float().t()
+    if b is not None:
+        ref = ref + b
+    if act:
+        ref = torch.nn.functional.gelu(ref)
+    if r is not None:
+        ref = ref + r.float()
+    assert D.shape == (M, N) and D.dtype == torch.bfloat16
+    assert rel_l2(D.float(), ref) < 4e-3            # bf16 output rounding only (2^-9 relative)
+    assert (D.float() - ref).abs().max().item() < 0.05 * max(1.0, ref.abs().max().item())
+
+
+def test_gemm_linearity_large(dev):
+    """Size-independent property at a bench-size problem: D(A1 + A2) == D(A1) + D(A2) (no bias)."""
+    eng = pkg.Engine(64, 0, 2, 1)
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 65536, 384, 96
+    A1 = torch.randn(M, K, generator=g).to(torch.bfloat16).to(dev)
+    A2 = (torch.randn(M, K, generator=g) * 2 ** -9).to(torch.bfloat16).to(dev)   # keeps A1 + A2 exact in bf16? no: compare in fp32
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(dev)
+    d1 = eng.gemm(A1, W).float()
+    d2 = eng.gemm(A2, W).float()
+    d12 = eng.gemm((A1.float() + A2.float()).to(torch.bfloat16), W).float()
+    ref12 = (A1.float() + A2.float()).to(torch.bfloat16).float() @ W.float().t()
+    assert rel_l2(d12, ref12) < 4e-3
+    assert rel_l2(d1 + d2, A1.float() @ W.float().t() + A2.float() @ W.float().t()) < 4e-3
+
+
+# ------------------------------------------------------------------ units, isolated
+def _nhwc(t, dev):
+    return t.permute(0, 2, 3, 1).contiguous().reshape(t.shape[0], -1).to(torch.bfloat16).to(dev)
+
+
+def test_every_unit_isolated_256(eng256, oracle256, dev):
+    ref, col = oracle256
+    x = fx.synthetic_images(1, 256)
+    prev = None
+    worst = {}
+    for u in eng256.units():
+        name = u["name"]
+        if name == "stem":
+            xin, want = x.to(dev), col["stem"].permute(0, 2, 3, 1)
+        elif name == "conv_exp":
+            xin, want = _nhwc(prev, dev), col["tokens"]
+        elif name == "projector":
+            xin, want = col["tokens"].reshape(1, -1).to(torch.bfloat16).to(dev), ref
+        else:
+            xin, want = _nhwc(prev, dev), col[name].permute(0, 2, 3, 1)
+        got = eng256.run_units(u["index"], u["index"], xin, 1)
+        assert got.shape == (1, u["out_elems"])
+        assert torch.isfinite(got.float()).all(), name
+        worst[name] = rel_l2(got.float().reshape(-1), want.reshape(-1))
+        prev = col.get(name)
+    bad = {k: v for k, v in worst.items() if v > UNIT_TOL}
+    assert not bad, bad
+
+
+# ------------------------------------------------------------------ end to end
+def test_encode_images_256_vs_oracle_and_reference_golden(eng256, oracle256, golden_dir, dev):
+    ref, col = oracle256
+    tokens, proj = eng256.forward(fx.synthetic_images(1, 256).to(dev), True, True)
+    assert tuple(tokens.shape) == (1, 16, 3072) and tuple(proj.shape) == (1, 16, 896)       # bit-exact shapes
+    assert rel_l2(tokens.float(), col["tokens"]) < E2E_TOL
+    assert rel_l2(proj.float(), ref) < E2E_TOL
+    g = np.load(os.path.join(golden_dir, "ref_256.npz"))                                      # unmodified reference
+    assert rel_l2(tokens.float(), g["tokens"]) < E2E_TOL
+    assert rel_l2(proj.float(), g["projected"]) < E2E_TOL
+
+
+def test_tokens_1024_vs_reference_golden(packed, golden_dir, dev):
+    eng = pkg.Engine(1024, 0, 2, 1).load({k: v for k, v in packed.items() if not k.startswith("projector")}, dev)
+    tokens, _ = eng.forward(fx.synthetic_images(1, 1024).to(dev), True, False)
+    assert tuple(tokens.shape) == (1, 256, 3072)                                              # FastVLM.swift:303
+    ref = np.load(os.path.join(golden_dir, "ref_1024_tokens.npy"))
+    assert rel_l2(tokens.float(), ref) < E2E_TOL
+
+
+def test_input_dtypes_and_batch_chunking(eng256, dev):
+    """fp32 / fp16 / bf16 images; B=5 with max_batch=2 (3 passes) == per-image results, bit-exact."""
+    x = fx.synthetic_images(5, 256, seed=11)
+    t32, p32 = eng256.forward(x.to(dev), True, True)
+    t16, _ = eng256.forward(x.half().to(dev), True, False)
+    tbf, _ = eng256.forward(x.bfloat16().to(dev), True, False)
+    assert rel_l2(t16.float(), t32.float()) < 1e-2 and rel_l2(tbf.float(), t32.float()) < 2e-2
+    for i in range(5):
+        ti, pi = eng256.forward(x[i:i + 1].to(dev), True, True)
+        assert torch.equal(ti[0], t32[i]) and torch.equal(pi[0], p32[i])                      # images are independent
+    with pytest.raises(pkg.FvhdError):
+        eng256.forward(torch.rand(1, 3, 128, 128, device=dev))                                # wrong R
+
+
+def test_host_entry_matches_device_entry(eng256, dev):
+    x = fx.synthetic_images(2, 256, seed=3)
+    _, proj = eng256.forward(x.to(dev), False, True)
+    host_in = x.half().pin_memory()
+    host_out = eng256.encode_images_host(host_in)
+    _, proj16 = eng256.forward(x.half().to(dev), False, True)
+    assert torch.equal(host_out, proj16.cpu())
+    assert rel_l2(host_out.float(), proj.float()) < 1e-2
+
+
+def test_missing_weights_and_workspace_fail_loudly(packed, dev):
+    eng = pkg.Engine(256, 896, 2, 1)
+    with pytest.raises(pkg.FvhdError):
+        eng.load({k: v for k, v in packed.items() if k != "network.4.7.fc1.w"}, dev)
+    with pytest.raises(pkg.FvhdError):
+        pkg.Engine(256, 0, 2, 1).forward(torch.rand(1, 3, 256, 256, device=dev))            # load() not called
+
+
+# ------------------------------------------------------------------ drop-in modules
+class _Args:
+    mm_vision_tower = "mobileclip_l_256"
+    unfreeze_mm_vision_tower = False
+    mm_projector_type = "mlp2x_gelu"
+    mm_hidden_size = 3072
+    hidden_size = 896
+
+
+def test_tower_and_projector_modules(tower_sd, proj_sd, oracle256, golden_dir, dev):
+    ref, col = oracle256
+    tower = pkg.build_vision_tower(_Args())
+    tower.load_state_dict(tower_sd, strict=True)
+    proj = pkg.build_vision_projector(_Args())
+    proj.load_state_dict(proj_sd, strict=True)
+    tower.to(device=dev, dtype=torch.bfloat16)          # llava/model/builder.py:173 does .to(device, dtype)
+    proj.to(device=dev, dtype=torch.bfloat16)
+    x = fx.synthetic_images(2, 256, seed=7)
+    g = np.load(os.path.join(golden_dir, "ref_b2_256.npz"))
+    feats = tower(x.to(dev))                            # fp32 images -> features come back in images.dtype
+    assert feats.dtype == torch.float32 and tuple(feats.shape) == (2, 16, 3072)
+    assert rel_l2(feats, g["tokens"]) < E2E_TOL
+    lst = tower([x[0].to(dev), x[1].to(dev)])           # list branch (mobileclip_encoder.py:78-83)
+    assert isinstance(lst, list) and tuple(lst[0].shape) == (1, 16, 3072)
+    assert rel_l2(lst[1], g["list1"]) < E2E_TOL
+
+    class Model:                                        # the two accessors encode_images uses (llava_arch.py:141-144)
+        def __init__(self):
+            self.mm_projector = proj
+        def get_model(self):
+            return self
+        def get_vision_tower(self):
+            return tower
+    m = Model()
+    fused = pkg.encode_images(m, fx.synthetic_images(1, 256).to(dev))
+    split = proj(tower(fx.synthetic_images(1, 256).to(dev)))
+    assert tuple(fused.shape) == (1, 16, 896)
+    assert rel_l2(fused, ref) < E2E_TOL and rel_l2(split, ref) < E2E_TOL
+    assert rel_l2(fused, split) < 5e-3                  # same kernels; split path rounds tokens through fp32->bf16 once more
+
+
+# ------------------------------------------------------------------ bench-size properties (R=1024)
+def test_batch_independence_and_determinism_1024(packed, dev):
+    eng = pkg.Engine(1024, 896, 2, 2).load(packed, dev)
+    x = fx.synthetic_images(2, 1024, seed=5).to(dev)
+    t, p = eng.forward(x, True, True)
+    t2, p2 = eng.forward(x, True, True)
+    assert torch.equal(t, t2) and torch.equal(p, p2)                          # deterministic (no atomics on the path)
+    ts, ps = eng.forward(x.flip(0), True, True)
+    assert torch.equal(ts.flip(0), t) and torch.equal(ps.flip(0), p)          # image i's tokens do not depend on its batch slot
+    assert torch.isfinite(p.float()).all()

@@ -1,0 +1,134 @@
+"""CPU tests of the host side: packer folds, arch key table, C-ABI symbol export, plan introspection,
+tower/projector drop-in surface.  No compute calls into the CUDA library (no GPU here)."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+import ml_fastvlm_b200 as pkg
+from ml_fastvlm_b200 import lib as L
+from oracle import fastvithd_oracle as orc
+from oracle import fixture as fx
+
+from . import packed_model
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel_l2(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+
+def test_arch_keys_match_reference(golden_dir):
+    keys = json.load(open(os.path.join(golden_dir, "keys.json")))
+    specs = pkg.reference_param_specs()
+    assert [k for k, _, _ in keys["tower"]] == list(specs.keys())
+    for k, shape, dtype in keys["tower"]:
+        assert list(specs[k][0]) == shape and str(specs[k][1]) == dtype, k
+    pspecs = pkg.projector_param_specs(3072, 896, 2)
+    assert [k for k, _, _ in keys["projector"]] == list(pspecs.keys())
+
+
+def test_packer_folds_reproduce_oracle(tower_sd, proj_sd):
+    """BN fold, layer-scale folds and layout changes are exact up to bf16 rounding of the GEMM weights."""
+    pk = pkg.pack_tower(tower_sd)
+    pk.update(pkg.pack_projector(proj_sd))
+    x = fx.synthetic_images(1, 256)
+    col_o, col_p = {}, {}
+    with torch.no_grad():
+        ref = orc.encode_images(x, tower_sd, proj_sd, col_o)
+        tokens, proj = packed_model.forward(x, pk, col_p)
+    for name in ["stem", "network.0", "network.2", "network.4", "network.7", "network.10"]:
+        assert rel_l2(col_p[name].permute(0, 3, 1, 2), col_o[name]) < 1e-2, name
+    assert rel_l2(tokens, col_o["tokens"]) < 1e-2       # only the bf16 weight rounding separates them
+    assert rel_l2(proj, ref) < 1e-2
+
+
+def test_packer_accepts_checkpoint_prefixes(tower_sd):
+    small = {("model.vision_tower." + k): v for k, v in tower_sd.items()}
+    a = pkg.pack_tower(small)
+    b = pkg.pack_tower(tower_sd)
+    assert list(a.keys()) == list(b.keys())
+    assert torch.equal(a["network.4.3.fc2.w"], b["network.4.3.fc2.w"])
+    with pytest.raises(KeyError):
+        pkg.pack_tower({"foo": torch.zeros(1)})
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "fastvithd_b200.h")).read()
+    declared = set(re.findall(r"\b(fvhd_[a-z_]+)\s*\(", header))
+    assert declared == set(L.SYMBOLS), declared ^ set(L.SYMBOLS)
+    lib = ctypes.CDLL(pkg.library_path())
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert pkg.load_library().fvhd_api_version() == 1
+
+
+def test_plan_matches_packer_and_survey(tower_sd, proj_sd):
+    eng = pkg.Engine(1024, 896, 2, 1)
+    specs = eng.weight_specs()
+    pk = pkg.pack_tower(tower_sd)
+    pk.update(pkg.pack_projector(proj_sd))
+    assert [n for n, _, _ in specs] == list(pk.keys())
+    for n, dt, numel in specs:
+        assert pk[n].numel() == numel and pk[n].dtype == (torch.float32 if dt == L.F32 else torch.bfloat16), n
+    units = eng.units()
+    assert [u["name"] for u in units][:3] == ["stem", "network.0.0", "network.0.1"]
+    assert units[-1]["name"] == "projector" and units[-2]["name"] == "conv_exp"
+    assert eng.num_tokens == 256 and eng.out_dim == 896
+    tower_gmacs = sum(u["flops"] for u in units[:-1]) / 2e9
+    assert abs(tower_gmacs - orc.gmacs_per_image(1024)) < 1e-6          # 243.35 GMAC
+    assert units[-2]["out_h"] * units[-2]["out_w"] == 256 and units[-2]["out_c"] == 3072
+    assert eng.workspace_bytes(1) > 9 * 65536 * 96 * 2
+
+
+def test_create_rejects_bad_configs():
+    for bad in [(100, 0, 2, 1), (1024, 7, 2, 1), (1024, 896, 3, 1), (1024, 0, 2, 0)]:
+        with pytest.raises(pkg.FvhdError):
+            pkg.Engine(*bad)
+
+
+def test_tower_drop_in_surface(tower_sd):
+    class Args:
+        mm_vision_tower = "mobileclip_l_256"
+        unfreeze_mm_vision_tower = False
+    lazy = pkg.build_vision_tower(Args(), delay_load=True)
+    assert not lazy.is_loaded and lazy.hidden_size == 3072 and lazy.config["image_cfg"]["patch_size"] == 64
+    tower = pkg.build_vision_tower(Args())
+    assert tower.is_loaded and tower.num_patches == 16 and tower.num_patches_per_side == 4
+    assert tower.config["image_cfg"]["image_size"] == 256
+    assert list(tower.state_dict().keys()) == list(tower_sd.keys())
+    tower.load_state_dict(tower_sd, strict=True)
+    assert tower.dtype == torch.float32 and tower.device.type == "cpu"
+    assert tuple(tower.dummy_feature.shape) == (1, 3072)
+    assert tower.image_processor.crop_size == {"height": 256, "width": 256}
+    assert list(tower.image_processor.image_mean) == [0.0, 0.0, 0.0]
+    with pytest.raises(pkg.FvhdError):          # no CPU fallback
+        tower(torch.rand(1, 3, 256, 256))
+    with pytest.raises(ValueError):
+        class Bad:
+            mm_vision_tower = "openai/clip-vit-large-patch14"
+        pkg.build_vision_tower(Bad())
+
+
+def test_projector_drop_in_surface(proj_sd):
+    class Cfg:
+        mm_projector_type = "mlp2x_gelu"
+        mm_hidden_size = 3072
+        hidden_size = 896
+    proj = pkg.build_vision_projector(Cfg())
+    assert list(proj.state_dict().keys()) == ["0.weight", "0.bias", "2.weight", "2.bias"]
+    proj.load_state_dict(proj_sd, strict=True)
+    with pytest.raises(pkg.FvhdError):
+        proj(torch.rand(1, 16, 3072))
+    Cfg.mm_projector_type = "linear"
+    assert list(pkg.build_vision_projector(Cfg()).state_dict().keys()) == ["weight", "bias"]
+    Cfg.mm_projector_type = "identity"
+    x = torch.rand(2, 3)
+    assert pkg.build_vision_projector(Cfg())(x) is x
+    Cfg.mm_projector_type = "bogus"
+    with pytest.raises(ValueError):
+        pkg.build_vision_projector(Cfg())
