@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- FastViTHD images/sec @1024 px (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py --gpus N --steps K --warmup W            # B200-native arm (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the reference algorithm on host cores
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
+
+A step = one pass of the hot path (`encode_images`: FastViTHD tower + mlp2x_gelu projector, H=896 as in
+FastVLM-0.5B) over one batch of synthetic 1024x1024 images (BASELINE.json configs[1]: batch 1 per GPU,
+random-init fixture weights, bf16 compute).  Multi-GPU: images shard by batch, one process per GPU,
+no collective on the data path (weak scaling).
+
+  value      images/s, inputs already resident in HBM, CUDA events per step, max over ranks,
+             L2 flushed (256 MiB write) between timed steps.
+  e2e        same metric through the host-buffer C-ABI entry (fvhd_encode_images_host): pinned fp16 host
+             images -> H2D -> forward -> D2H of the projected tokens, all inside the timed region.
+  roofline   dominant kernel (tcgen05 GEMM): algorithmic FLOPs of all its launches in one step / their
+             summed live CUDA-event durations, against the measured bf16 peak (MEASURED_PEAKS.json).
+  cpu_baseline  oracle port (fp32 torch CPU restatement of the reference) timed on the host cores, N=1 only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RES = 1024
+HIDDEN = 896            # Qwen2-0.5B hidden size (FastVLM-0.5B projector output)
+METRIC = "fastvithd_images_per_sec_1024px"
+UNIT = "images/s"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}    # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def _host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        return os.cpu_count() or 1
+
+
+def cpu_reference_time(steps, warmup):
+    """The reference algorithm (oracle port: same ATen fp32 ops as the reference's torch.nn modules) on the host cores.
+    oneDNN does not scale monotonically with threads on many-core hosts (128 threads measured 10x slower than 8),
+    so the thread count is calibrated first on a 512-px image over {8,16,32,64,all} and the fastest is used
+    -- the reference gets its best configuration; `cores` reports the threads actually used."""
+    import torch
+    from oracle import fastvithd_oracle as orc
+    from oracle import fixture as fx
+    cores = _host_cores()
+    sd = fx.tower_state_dict()
+    psd = fx.projector_state_dict(HIDDEN)
+    cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
+    best, best_t = cands[0], None
+    xs = fx.synthetic_images(1, 512)
+    with torch.inference_mode():
+        for c in cands:
+            torch.set_num_threads(c)
+            orc.encode_images(xs, sd, psd)
+            t0 = time.perf_counter()
+            orc.encode_images(xs, sd, psd)
+            dt = time.perf_counter() - t0
+            if best_t is None or dt < best_t:
+                best, best_t = c, dt
+        torch.set_num_threads(best)
+        x = fx.synthetic_images(1, RES)
+        for _ in range(warmup):
+            orc.encode_images(x, sd, psd)
+        times = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            orc.encode_images(x, sd, psd)
+            times.append(time.perf_counter() - t0)
+    return times, best
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = max(1, args.steps)
+    warmup = max(1, min(args.warmup, 2))
+    times, cores = cpu_reference_time(steps, warmup)
+    ms = 1e3 * sum(times) / len(times)
+    val = 1e3 / ms
+    sample = f"{steps} steps x 1 image {RES}x{RES} fp32 (+{warmup} warm-up), oracle port of the reference modules, torch CPU, {cores} threads (calibrated best of 8/16/32/64/all)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"encode_images: FastViTHD tower + mlp2x_gelu projector (H={HIDDEN}), batch 1, {RES}x{RES}", "resolution": RES,
+                   "batch_per_gpu": 1, "weights": "seeded random fixture"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "min_ms": 1e3 * min(times), "median_ms": 1e3 * statistics.median(times)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args):
+    import torch
+    import ml_fastvlm_b200 as pkg
+    from oracle import fixture as fx
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"WORLD_SIZE {world} != --gpus {args.gpus}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch N>1 with torch.distributed.run (one process per GPU)")
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    sd = fx.tower_state_dict()
+    psd = fx.projector_state_dict(HIDDEN)
+    packed = pkg.pack_tower(sd)
+    packed.update(pkg.pack_projector(psd))
+    eng = pkg.Engine(RES, HIDDEN, 2, B).load(packed, dev)
+    del sd, psd
+
+    host_img = fx.synthetic_images(B, RES, seed=100 + rank).half().pin_memory()
+    dev_img = host_img.to(dev).to(torch.bfloat16)            # resident input for `value`
+    host_out = torch.empty(B, eng.num_tokens, HIDDEN, dtype=torch.bfloat16).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for _ in range(warmup):
+        eng.forward(dev_img, want_tokens=False, want_projected=True)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        flush.fill_(i & 0xFF)                               # L2 flush, outside the timed bracket
+        ev[i][0].record()
+        eng.forward(dev_img, want_tokens=False, want_projected=True)
+        ev[i][1].record()
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
+
+    # ---- end to end through the host-buffer entry (H2D + forward + D2H inside the timed region)
+    for _ in range(2):
+        eng.encode_images_host(host_img, host_out)
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        eng.encode_images_host(host_img, host_out)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms_evt = e0.elapsed_time(e1)
+    e2e_ms_wall = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e2e_ms_evt, e2e_ms_wall)
+    clocks = sampler.stop()
+
+    # ---- max over ranks
+    if dist is not None:
+        t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = t[0].item(), t[1].item()
+
+    line = None
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        # ---- per-kernel live timing (CUDA events around each launch) -> roofline of the dominant kernel
+        eng.profile_steps(dev_img)
+        reps = 5
+        acc = None
+        for _ in range(reps):
+            flush.fill_(1)
+            ms = eng.profile_steps(dev_img)
+            acc = ms if acc is None else [a + b for a, b in zip(acc, ms)]
+        ms = [a / reps for a in acc]
+        info = eng.steps(B)
+        kernels = {}
+        for st, m in zip(info, ms):
+            k = kernels.setdefault(st["kernel"], {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            k["launches"] += 1
+            k["ms"] += m
+            k["flops"] += st["flops"]
+            k["bytes"] += st["bytes"]
+        ktab = []
+        for name, k in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"]):
+            ktab.append({"kernel": name, "launches": k["launches"], "ms": round(k["ms"], 4), "share": round(k["ms"] / sum(ms), 4),
+                         "tflops": round(k["flops"] / k["ms"] / 1e9, 1) if k["ms"] > 0 else None,
+                         "gbs": round(k["bytes"] / k["ms"] / 1e6, 1) if k["ms"] > 0 else None})
+        gk = kernels["gemm_bf16_tcgen05_kernel"]
+        ach = gk["flops"] / gk["ms"] / 1e9           # TFLOP/s
+        peak = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
+        roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
+                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": f"{peak_src} (burst bf16 GEMM)",
+                    "launches_per_step": gk["launches"], "avg_launch_us": round(1e3 * gk["ms"] / gk["launches"], 2),
+                    "algorithmic_flops_per_step": gk["flops"], "share_of_step": round(gk["ms"] / sum(ms), 4)}
+        # whole-step view against both roofs: F = 488.5 GFLOP, B_act + W bytes
+        units = eng.units()
+        F = sum(u["flops"] for u in units) * B
+        step_ms_mean = total_ms / steps
+        whole = {"tflops": round(F / step_ms_mean / 1e9, 1), "frac_of_bf16_peak": round(F / step_ms_mean / 1e9 / peak, 4),
+                 "t_tensor_roof_ms": round(F / peak / 1e9, 4), "sum_kernel_ms": round(sum(ms), 4)}
+        value = world * B * steps / (total_ms / 1e3)
+        e2e_val = world * B * steps / (e2e_ms / 1e3)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            times, cores = cpu_reference_time(args.cpu_steps, 1)
+            cms = 1e3 * sum(times) / len(times)
+            cpu = {"value": 1e3 / cms, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{args.cpu_steps} images {RES}x{RES} fp32 (+1 warm-up) through the oracle port (torch CPU, {cores} threads = calibrated best of 8/16/32/64/all)",
+                   "ms_per_image": cms}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"encode_images: FastViTHD tower + mlp2x_gelu projector (H={HIDDEN}), batch {B} per GPU, {RES}x{RES}",
+                       "resolution": RES, "batch_per_gpu": B, "global_batch": B * world, "weights": "seeded random fixture",
+                       "parallelism": f"batch-sharded x{world}, no data-path collective", "l2": "flushed (256 MiB write) between timed steps",
+                       "input": "bf16 NCHW resident in HBM (value); pinned fp16 host (e2e)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": host_img.numel() * 2, "d2h_bytes_per_step": host_out.numel() * 2,
+                    "ms_per_step": e2e_ms / steps, "api": "fvhd_encode_images_host (C ABI) via Engine.encode_images_host"},
+            "gpu_launches": eng.launches_per_forward(B) * steps,
+            "roofline": roofline, "whole_step": whole, "kernels": ktab,
+            "step_ms_min": min(step_ms), "step_ms_median": statistics.median(step_ms),
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="images per GPU per step (BASELINE configs[1]: 1)")
+    ap.add_argument("--cpu-steps", type=int, default=5, help="images timed for cpu_baseline (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 50:
+            args.steps = 8
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

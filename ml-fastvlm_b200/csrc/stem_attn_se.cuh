@@ -30,12 +30,12 @@ __global__ void __launch_bounds__(STEM_THREADS)
 stem_kernel(const T* __restrict__ img, bf16* __restrict__ out, const float* __restrict__ w0 /*[27][96], k=(ci*3+ky)*3+kx*/,
             const float* __restrict__ b0, const float* __restrict__ w1 /*[9][96]*/, const float* __restrict__ b1, int R, int tiles_x) {
     extern __shared__ __align__(16) float stem_smem[];
-    float* sin = stem_smem;                                              // [3][35][36]
-    uint32_t* s1 = reinterpret_cast<uint32_t*>(sin + 3 * STEM_IN * STEM_INP);   // [289][49]
-    float* w0s = reinterpret_cast<float*>(s1 + STEM_MID * STEM_MID * STEM_MIDP);
-    float* w1s = w0s + 27 * STEM_C;
+    float* w0s = stem_smem;                                              // [27][96], float4 reads: 16-B aligned at the base
+    float* w1s = w0s + 27 * STEM_C;                                      // [9][96]
     float* b0s = w1s + 9 * STEM_C;
     float* b1s = b0s + STEM_C;
+    float* sin = b1s + STEM_C;                                           // [3][35][36]
+    uint32_t* s1 = reinterpret_cast<uint32_t*>(sin + 3 * STEM_IN * STEM_INP);   // [289][49]
 
     const int b = blockIdx.z;
     const int ty0 = (blockIdx.x / tiles_x) * STEM_TO, tx0 = (blockIdx.x % tiles_x) * STEM_TO;
