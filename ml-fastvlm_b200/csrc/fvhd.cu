@@ -7,6 +7,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -30,8 +31,7 @@ std::string g_create_error;
 struct WeightSpec { std::string name; int dtype; int64_t numel; };
 
 struct RunCtx {
-    const void* images; int img_dtype;
-    void* final_out;            // destination of the last unit's output when it is user memory (or nullptr)
+    int img_dtype;              // selects the stem instantiation; every pointer goes through the device IoBlock
 };
 typedef std::function<cudaError_t(cudaStream_t, const RunCtx&)> Step;
 
@@ -52,6 +52,8 @@ struct Plan {                   // launch sequence for one batch size
     std::vector<bf16*> unit_in, unit_out;          // workspace buffers per unit
     struct Info { const char* kernel; int unit; double flops; double bytes; };
     std::vector<Info> info;                        // one per step (== one kernel launch)
+    IoBlock* io = nullptr;                         // device IO block of this plan (in the workspace)
+    std::map<int, cudaGraphExec_t> graphs;         // key: img_dtype | last_step << 2 | copy_tokens << 20
     void add(const Step& s, const char* kernel, int unit, double flops, double bytes) {
         steps.push_back(s);
         info.push_back({kernel, unit, flops, bytes});
@@ -76,6 +78,9 @@ struct fvhd_handle_s {
     void* ws = nullptr;
     size_t ws_bytes = 0;
     EncodeTiledFn encode = nullptr;
+    int num_sms = 148;
+    bool use_graph = true;
+    cudaStream_t cap_stream = nullptr;   // private stream used only to capture graphs (the legacy default stream cannot be captured)
     std::map<int, Plan> plans;
     int64_t act0 = 0;           // elements of the largest activation per image: (R/4)^2 * 96
     void *stage_in = nullptr, *stage_out = nullptr;   // fvhd_encode_images_host device staging
@@ -222,11 +227,12 @@ void build_arch(fvhd_handle h) {
 struct Buffers {
     bf16 *X0, *X1, *Y, *Z, *T1, *H4;
     float *pooled, *sr;
+    IoBlock* io;
 };
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 size_t workspace_bytes(fvhd_handle h, int batch) {
     const size_t a = align_up((size_t)h->act0 * batch * 2, 1024);
-    return 9 * a + align_up((size_t)batch * 3072 * 4, 1024) + align_up((size_t)batch * kSeRd * 4, 1024) + 1024;
+    return 9 * a + align_up((size_t)batch * 3072 * 4, 1024) + align_up((size_t)batch * kSeRd * 4, 1024) + 1024 /*io block*/ + 1024;
 }
 Buffers carve(fvhd_handle h, int batch) {
     const size_t a = align_up((size_t)h->act0 * batch * 2, 1024);
@@ -239,7 +245,8 @@ Buffers carve(fvhd_handle h, int batch) {
     b.T1 = (bf16*)p; p += a;
     b.H4 = (bf16*)p; p += 4 * a;
     b.pooled = (float*)p; p += align_up((size_t)batch * 3072 * 4, 1024);
-    b.sr = (float*)p;
+    b.sr = (float*)p; p += align_up((size_t)batch * kSeRd * 4, 1024);
+    b.io = (IoBlock*)p;
     return b;
 }
 
@@ -260,6 +267,8 @@ int ensure_cuda(fvhd_handle h) {
     CUDA_TRY(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     if (!fn || qres != cudaDriverEntryPointSuccess) return fail(h, FVHD_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    h->num_sms = prop.multiProcessorCount;
+    { const char* e = getenv("FVHD_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
     CUDA_TRY(h, set_smem(gemm_bf16_tcgen05_kernel, 227 * 1024));
     CUDA_TRY(h, set_smem(repmixer_dw_kernel, MixCfg::SMEM));
     CUDA_TRY(h, set_smem(dwconv_kernel<7, 1, 1, 0, 16, 16, 8>, DwCfg<7, 1, 1, 16, 16>::SMEM));
@@ -268,6 +277,7 @@ int ensure_cuda(fvhd_handle h) {
     CUDA_TRY(h, set_smem(stem_kernel<float>, STEM_SMEM));
     CUDA_TRY(h, set_smem(stem_kernel<__half>, STEM_SMEM));
     CUDA_TRY(h, set_smem(stem_kernel<bf16>, STEM_SMEM));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
     h->cuda_ready = true;
     return FVHD_OK;
 }
@@ -287,34 +297,45 @@ int make_tmap(fvhd_handle h, CUtensorMap* m, const void* ptr, int64_t rows, int6
     return FVHD_OK;
 }
 
-int pick_bn(int N) {
-    if (N % 128 == 0) return 128;
-    if (N % 96 == 0 && N <= 256) return 96;
-    if (N % 64 == 0) return 64;
-    if (N >= 128) return 128;
-    return ((N + 31) / 32) * 32;
+// Tile-shape heuristic: minimise waves x (BN + fixed per-tile cost), prefer the larger tile on ties.
+int pick_bn(int M, int N, int num_sms) {
+    const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+    const int cands[5] = {256, 128, 96, 64, 32};
+    int best = 128;
+    long best_cost = -1;
+    for (int bn : cands) {
+        if (bn == 96 && N % 96) continue;               // 96 only when it divides N (C = 96 / 192 / 384 layers)
+        if (bn == 256 && N % 256) continue;
+        if (bn > 32 && bn > ((N + 31) / 32) * 32) continue;
+        const long tiles = (long)tiles_m * ((N + bn - 1) / bn);
+        const long waves = (tiles + num_sms - 1) / num_sms;
+        const long cost = waves * (bn + 24);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+    }
+    return best;
 }
 
 // Build one GEMM launch step.  D may be nullptr => taken from RunCtx.final_out at launch time.
-int make_gemm_step(fvhd_handle h, Step* out, const bf16* A, int lda, const bf16* W, const float* bias, const bf16* residual, int ldr,
+int make_gemm_step(fvhd_handle h, Step* out, const IoBlock* io, const bf16* A, int lda, const bf16* W, const float* bias, const bf16* residual, int ldr,
                    bf16* D, int ldd, int M, int N, int K, int act) {
     if (N % 8 || K % 8) return fail(h, FVHD_ERR_INVALID, "GEMM N (%d) and K (%d) must be multiples of 8", N, K);
     GemmParams p{};
     p.M = M; p.N = N; p.K = K;
-    p.BN = pick_bn(N);
+    p.BN = pick_bn(M, N, h->num_sms);
     const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
-    p.stages = num_kb < 3 ? num_kb : 3;
-    p.D = D; p.ldd = ldd; p.bias = bias; p.residual = residual; p.ldr = ldr; p.act = act;
+    p.stages = gemm_pick_stages(p.BN, num_kb);
+    p.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+    p.tiles_n = (N + p.BN - 1) / p.BN;
+    p.D = D; p.io = io; p.ldd = ldd; p.bias = bias; p.residual = residual; p.ldr = ldr; p.act = act;
     CUtensorMap ta, tb;
     int rc;
     if ((rc = make_tmap(h, &ta, A, M, K, lda, GEMM_BM)) != FVHD_OK) return rc;
     if ((rc = make_tmap(h, &tb, W, N, K, K, p.BN)) != FVHD_OK) return rc;
-    const dim3 grid((N + p.BN - 1) / p.BN, (M + GEMM_BM - 1) / GEMM_BM);
+    const int tiles = p.tiles_m * p.tiles_n;
+    const dim3 grid(tiles < h->num_sms ? tiles : h->num_sms);
     const size_t smem = gemm_smem_bytes(p.BN, p.stages);
-    *out = [=](cudaStream_t s, const RunCtx& ctx) -> cudaError_t {
-        GemmParams q = p;
-        if (!q.D) q.D = reinterpret_cast<bf16*>(ctx.final_out);
-        gemm_bf16_tcgen05_kernel<<<grid, GEMM_THREADS, smem, s>>>(ta, tb, q);
+    *out = [=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+        gemm_bf16_tcgen05_kernel<<<grid, GEMM_THREADS, smem, s>>>(ta, tb, p);
         return cudaGetLastError();
     };
     return FVHD_OK;
@@ -342,7 +363,7 @@ double gemm_bytes(double M, double N, double K, bool res) { return 2.0 * (M * K 
 int add_gemm(fvhd_handle h, Plan& pl, int unit, const bf16* A, int lda, const bf16* W, const float* bias, const bf16* residual, int ldr,
              bf16* D, int ldd, int M, int N, int K, int act) {
     Step g;
-    int rc = make_gemm_step(h, &g, A, lda, W, bias, residual, ldr, D, ldd, M, N, K, act);
+    int rc = make_gemm_step(h, &g, pl.io, A, lda, W, bias, residual, ldr, D, ldd, M, N, K, act);
     if (rc != FVHD_OK) return rc;
     pl.add(g, kGemm, unit, gemm_flops(M, N, K), gemm_bytes(M, N, K, residual != nullptr));
     return FVHD_OK;
@@ -358,6 +379,8 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
     pl = Plan();
     pl.batch = batch;
     const Buffers bf = carve(h, batch);
+    pl.io = bf.io;
+    const IoBlock* io = bf.io;
     bf16* cur = bf.X0;
     bf16* nxt = bf.X1;
     int rc;
@@ -380,9 +403,9 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
             const dim3 grid(tiles * tiles, 1, batch);
             bf16* t0 = bf.T1;
             pl.add([=](cudaStream_t s, const RunCtx& ctx) -> cudaError_t {
-                if (ctx.img_dtype == FVHD_F32) stem_kernel<float><<<grid, STEM_THREADS, STEM_SMEM, s>>>((const float*)ctx.images, t0, w0, b0, w1, b1, R, tiles);
-                else if (ctx.img_dtype == FVHD_F16) stem_kernel<__half><<<grid, STEM_THREADS, STEM_SMEM, s>>>((const __half*)ctx.images, t0, w0, b0, w1, b1, R, tiles);
-                else stem_kernel<bf16><<<grid, STEM_THREADS, STEM_SMEM, s>>>((const bf16*)ctx.images, t0, w0, b0, w1, b1, R, tiles);
+                if (ctx.img_dtype == FVHD_F32) stem_kernel<float><<<grid, STEM_THREADS, STEM_SMEM, s>>>(io, t0, w0, b0, w1, b1, R, tiles);
+                else if (ctx.img_dtype == FVHD_F16) stem_kernel<__half><<<grid, STEM_THREADS, STEM_SMEM, s>>>(io, t0, w0, b0, w1, b1, R, tiles);
+                else stem_kernel<bf16><<<grid, STEM_THREADS, STEM_SMEM, s>>>(io, t0, w0, b0, w1, b1, R, tiles);
                 return cudaGetLastError();
             }, "stem_kernel", U, 2.0 * batch * ((double)(R / 2) * (R / 2) * 96 * 27 + (double)(R / 4) * (R / 4) * 96 * 9),
                (double)batch * (3.0 * R * R * 2 + (double)(R / 4) * (R / 4) * 96 * 2));
@@ -453,9 +476,8 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
                 se_reduce_kernel<<<dim3(kSeRd / 8, batch), 256, 0, s>>>(pooled, wr, br, sr, 3072, kSeRd);
                 return cudaGetLastError();
             }, "se_reduce_kernel", U, 2.0 * batch * 3072 * kSeRd, 2.0 * 3072 * kSeRd);
-            pl.add([=](cudaStream_t s, const RunCtx& ctx) -> cudaError_t {
-                bf16* d = dst ? dst : reinterpret_cast<bf16*>(ctx.final_out);
-                se_expand_scale_gelu_kernel<<<dim3(3072 / 128, batch), 256, 0, s>>>(cexp, sr, we, be, d, HW, 3072, kSeRd);
+            pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+                se_expand_scale_gelu_kernel<<<dim3(3072 / 128, batch), 256, 0, s>>>(cexp, sr, we, be, dst, io, HW, 3072, kSeRd);
                 return cudaGetLastError();
             }, "se_expand_scale_gelu_kernel", U, 2.0 * batch * 3072 * kSeRd, 4.0 * Md * 3072 + 2.0 * 3072 * kSeRd);
             break;
@@ -506,13 +528,68 @@ int check_ready(fvhd_handle h, int batch) {
 
 size_t dtype_size(int dt) { return dt == FVHD_F32 ? 4 : 2; }
 
-// Run steps [s0, s1) of a plan.
+// Run steps [s0, s1) of a plan (direct launches).
 int run_steps(fvhd_handle h, Plan& pl, int s0, int s1, cudaStream_t st, const RunCtx& ctx) {
     for (int i = s0; i < s1; ++i) {
         cudaError_t e = pl.steps[i](st, ctx);
-        if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "launch of step %d failed: %s", i, cudaGetErrorString(e));
+        if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "launch of step %d (%s) failed: %s", i, pl.info[i].kernel, cudaGetErrorString(e));
     }
     return FVHD_OK;
+}
+
+int set_io(fvhd_handle h, Plan& pl, cudaStream_t st, const void* images, void* final_out, void* tokens_out) {
+    set_io_kernel<<<1, 1, 0, st>>>(pl.io, images, final_out, tokens_out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "set_io_kernel launch failed: %s", cudaGetErrorString(e));
+    return FVHD_OK;
+}
+
+int launch_copy_tokens(fvhd_handle h, Plan& pl, cudaStream_t st, const bf16* src, size_t bytes) {
+    const size_t n16 = bytes / 16;
+    int blocks = (int)((n16 + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    copy_tokens_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(src), pl.io, n16);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "copy_tokens_kernel launch failed: %s", cudaGetErrorString(e));
+    return FVHD_OK;
+}
+
+// Steps [0, last_step) (+ token copy-out) as ONE graph launch; captured once per (dtype, last_step, copy) and replayed.
+// Falls back to direct launches when graphs are disabled (FVHD_NO_GRAPH=1) or the caller is itself capturing `st`.
+int run_forward(fvhd_handle h, Plan& pl, cudaStream_t st, const RunCtx& ctx, int last_step, const bf16* tok_src, size_t tok_bytes) {
+    int rc;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (!h->use_graph || cs != cudaStreamCaptureStatusNone) {
+        if ((rc = run_steps(h, pl, 0, last_step, st, ctx)) != FVHD_OK) return rc;
+        if (tok_src) return launch_copy_tokens(h, pl, st, tok_src, tok_bytes);
+        return FVHD_OK;
+    }
+    const int key = ctx.img_dtype | (last_step << 2) | ((tok_src ? 1 : 0) << 20);
+    auto it = pl.graphs.find(key);
+    if (it == pl.graphs.end()) {
+        cudaGraph_t graph = nullptr;
+        cudaStream_t cap = h->cap_stream;
+        CUDA_TRY(h, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+        rc = run_steps(h, pl, 0, last_step, cap, ctx);
+        if (rc == FVHD_OK && tok_src) rc = launch_copy_tokens(h, pl, cap, tok_src, tok_bytes);
+        cudaError_t e = cudaStreamEndCapture(cap, &graph);
+        if (rc != FVHD_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        cudaGraphExec_t exec = nullptr;
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+        it = pl.graphs.emplace(key, exec).first;
+    }
+    CUDA_TRY(h, cudaGraphLaunch(it->second, st));
+    return FVHD_OK;
+}
+
+void destroy_plans(fvhd_handle h) {
+    for (auto& kv : h->plans)
+        for (auto& g : kv.second.graphs) cudaGraphExecDestroy(g.second);
+    h->plans.clear();
 }
 
 }  // namespace
@@ -541,6 +618,8 @@ int fvhd_create(const fvhd_config* cfg, fvhd_handle* out) {
 
 int fvhd_destroy(fvhd_handle h) {
     if (h) {
+        destroy_plans(h);
+        if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
         if (h->stage_in) cudaFree(h->stage_in);
         if (h->stage_out) cudaFree(h->stage_out);
     }
@@ -577,7 +656,7 @@ int fvhd_load_weights(fvhd_handle h, const fvhd_tensor* table, int n) {
         wp[s.name] = t->data;
     }
     h->wptr.swap(wp);
-    h->plans.clear();
+    destroy_plans(h);
     h->loaded = true;
     return FVHD_OK;
 }
@@ -592,7 +671,7 @@ int fvhd_set_workspace(fvhd_handle h, void* dptr, size_t bytes) {
     if (!h) return FVHD_ERR_INVALID;
     h->ws = dptr;
     h->ws_bytes = bytes;
-    h->plans.clear();
+    destroy_plans(h);
     return FVHD_OK;
 }
 
@@ -631,7 +710,7 @@ int fvhd_launches_per_forward(fvhd_handle h, int batch) {
         }
     }
     const int passes = (batch + h->cfg.max_batch - 1) / h->cfg.max_batch;
-    return steps * passes;
+    return (steps + 1 /*set_io_kernel*/) * passes;
 }
 
 int fvhd_forward(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch, void* tokens, void* projected) {
@@ -653,19 +732,19 @@ int fvhd_forward(fvhd_handle h, void* stream, const void* images, int img_dtype,
         Plan* pl;
         if ((rc = get_plan(h, bc, &pl)) != FVHD_OK) return rc;
         RunCtx ctx;
-        ctx.images = reinterpret_cast<const uint8_t*>(images) + (size_t)b0 * img_stride;
         ctx.img_dtype = img_dtype;
+        const void* img = reinterpret_cast<const uint8_t*>(images) + (size_t)b0 * img_stride;
         uint8_t* tok_dst = tokens ? reinterpret_cast<uint8_t*>(tokens) + (size_t)b0 * tok_stride : nullptr;
         uint8_t* prj_dst = projected ? reinterpret_cast<uint8_t*>(projected) + (size_t)b0 * prj_stride : nullptr;
         if (has_proj) {
-            // tokens stay in the workspace (the projector's TMA map points there); copy out if requested
+            // tokens stay in the workspace (the projector's TMA map points there); copied out if requested
             const int last_unit = projected ? nunits - 1 : nunits - 2;
-            ctx.final_out = prj_dst;
-            if ((rc = run_steps(h, *pl, 0, pl->unit_steps[last_unit].second, st, ctx)) != FVHD_OK) return rc;
-            if (tok_dst) CUDA_TRY(h, cudaMemcpyAsync(tok_dst, pl->unit_out[tok_unit], (size_t)bc * tok_stride, cudaMemcpyDeviceToDevice, st));
+            if ((rc = set_io(h, *pl, st, img, prj_dst, tok_dst)) != FVHD_OK) return rc;
+            if ((rc = run_forward(h, *pl, st, ctx, pl->unit_steps[last_unit].second, tok_dst ? pl->unit_out[tok_unit] : nullptr,
+                                  (size_t)bc * tok_stride)) != FVHD_OK) return rc;
         } else {
-            ctx.final_out = tok_dst;
-            if ((rc = run_steps(h, *pl, 0, (int)pl->steps.size(), st, ctx)) != FVHD_OK) return rc;
+            if ((rc = set_io(h, *pl, st, img, tok_dst, nullptr)) != FVHD_OK) return rc;
+            if ((rc = run_forward(h, *pl, st, ctx, (int)pl->steps.size(), nullptr, 0)) != FVHD_OK) return rc;
         }
     }
     return FVHD_OK;
@@ -714,18 +793,14 @@ int fvhd_run_units(fvhd_handle h, void* stream, int first, int last, const void*
     Plan* pl;
     if ((rc = get_plan(h, batch, &pl)) != FVHD_OK) return rc;
     RunCtx ctx;
-    ctx.images = in;
     ctx.img_dtype = img_dtype;
-    ctx.final_out = nullptr;
     if (first > 0)
         CUDA_TRY(h, cudaMemcpyAsync(pl->unit_in[first], in, (size_t)batch * h->units[first].in_elems * 2, cudaMemcpyDeviceToDevice, st));
     const size_t out_bytes = (size_t)batch * h->units[last].out_elems * 2;
-    if (last == nunits - 1) {
-        ctx.final_out = out;      // the last unit of the plan writes straight to the caller's buffer
-        return run_steps(h, *pl, pl->unit_steps[first].first, pl->unit_steps[last].second, st, ctx);
-    }
+    // the last unit of the plan writes straight to the caller's buffer; earlier units are copied out of the workspace
+    if ((rc = set_io(h, *pl, st, in, last == nunits - 1 ? out : nullptr, nullptr)) != FVHD_OK) return rc;
     if ((rc = run_steps(h, *pl, pl->unit_steps[first].first, pl->unit_steps[last].second, st, ctx)) != FVHD_OK) return rc;
-    CUDA_TRY(h, cudaMemcpyAsync(out, pl->unit_out[last], out_bytes, cudaMemcpyDeviceToDevice, st));
+    if (last != nunits - 1) CUDA_TRY(h, cudaMemcpyAsync(out, pl->unit_out[last], out_bytes, cudaMemcpyDeviceToDevice, st));
     return FVHD_OK;
 }
 
@@ -741,9 +816,8 @@ int fvhd_profile_units(fvhd_handle h, void* stream, const void* images, int img_
     std::vector<cudaEvent_t> ev(nunits + 1);
     for (auto& e : ev) CUDA_TRY(h, cudaEventCreate(&e));
     RunCtx ctx;
-    ctx.images = images;
     ctx.img_dtype = img_dtype;
-    ctx.final_out = pl->unit_out[nunits - 1];   // keep the final result inside the workspace
+    if ((rc = set_io(h, *pl, st, images, pl->unit_out[nunits - 1], nullptr)) != FVHD_OK) return rc;   // result stays in the workspace
     CUDA_TRY(h, cudaEventRecord(ev[0], st));
     for (int u = 0; u < nunits; ++u) {
         if ((rc = run_steps(h, *pl, pl->unit_steps[u].first, pl->unit_steps[u].second, st, ctx)) != FVHD_OK) return rc;
@@ -788,9 +862,8 @@ int fvhd_profile_steps(fvhd_handle h, void* stream, const void* images, int img_
     std::vector<cudaEvent_t> ev(n + 1);
     for (auto& e : ev) CUDA_TRY(h, cudaEventCreate(&e));
     RunCtx ctx;
-    ctx.images = images;
     ctx.img_dtype = img_dtype;
-    ctx.final_out = pl->unit_out[h->units.size() - 1];
+    if ((rc = set_io(h, *pl, st, images, pl->unit_out[h->units.size() - 1], nullptr)) != FVHD_OK) return rc;
     CUDA_TRY(h, cudaEventRecord(ev[0], st));
     for (int i = 0; i < n; ++i) {
         if ((rc = run_steps(h, *pl, i, i + 1, st, ctx)) != FVHD_OK) return rc;
@@ -807,7 +880,8 @@ int fvhd_gemm(fvhd_handle h, void* stream, const void* A, const void* W, const v
     int rc = ensure_cuda(h);
     if (rc != FVHD_OK) return rc;
     Step s;
-    if ((rc = make_gemm_step(h, &s, (const bf16*)A, K, (const bf16*)W, (const float*)bias, (const bf16*)residual, N, (bf16*)D, N, M, N, K, act)) != FVHD_OK) return rc;
+    if ((rc = make_gemm_step(h, &s, nullptr, (const bf16*)A, K, (const bf16*)W, (const float*)bias, (const bf16*)residual, N, (bf16*)D, N, M, N, K, act)) != FVHD_OK) return rc;
+    if (!D) return fail(h, FVHD_ERR_INVALID, "D is null");
     RunCtx ctx{};
     cudaError_t e = s(reinterpret_cast<cudaStream_t>(stream), ctx);
     if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "gemm launch failed: %s", cudaGetErrorString(e));

@@ -27,7 +27,7 @@ template <> __device__ __forceinline__ float img_ld<bf16>(const bf16* p) { retur
 
 template <typename T>
 __global__ void __launch_bounds__(STEM_THREADS)
-stem_kernel(const T* __restrict__ img, bf16* __restrict__ out, const float* __restrict__ w0 /*[27][96], k=(ci*3+ky)*3+kx*/,
+stem_kernel(const IoBlock* __restrict__ io, bf16* __restrict__ out, const float* __restrict__ w0 /*[27][96], k=(ci*3+ky)*3+kx*/,
             const float* __restrict__ b0, const float* __restrict__ w1 /*[9][96]*/, const float* __restrict__ b1, int R, int tiles_x) {
     extern __shared__ __align__(16) float stem_smem[];
     float* w0s = stem_smem;                                              // [27][96], float4 reads: 16-B aligned at the base
@@ -37,6 +37,7 @@ stem_kernel(const T* __restrict__ img, bf16* __restrict__ out, const float* __re
     float* sin = b1s + STEM_C;                                           // [3][35][36]
     uint32_t* s1 = reinterpret_cast<uint32_t*>(sin + 3 * STEM_IN * STEM_INP);   // [289][49]
 
+    const T* __restrict__ img = reinterpret_cast<const T*>(io->images);
     const int b = blockIdx.z;
     const int ty0 = (blockIdx.x / tiles_x) * STEM_TO, tx0 = (blockIdx.x % tiles_x) * STEM_TO;
     const int R2 = R / 2, R4 = R / 4;
@@ -354,7 +355,8 @@ se_reduce_kernel(const float* __restrict__ pooled, const bf16* __restrict__ wr /
 // grid (C/128, B): expand + sigmoid for a 128-channel slice, then scale + GELU all HW pixels of it.
 __global__ void __launch_bounds__(256)
 se_expand_scale_gelu_kernel(const bf16* __restrict__ c, const float* __restrict__ r, const bf16* __restrict__ we /*[C][RD]*/,
-                            const float* __restrict__ be, bf16* __restrict__ tokens, int HW, int C, int RD) {
+                            const float* __restrict__ be, bf16* __restrict__ tokens_or_null, const IoBlock* __restrict__ io, int HW, int C, int RD) {
+    bf16* __restrict__ tokens = tokens_or_null ? tokens_or_null : reinterpret_cast<bf16*>(io->final_out);
     __shared__ float rs[256];
     __shared__ float ss[128];
     const int b = blockIdx.y, c0 = blockIdx.x * 128;
@@ -378,6 +380,19 @@ se_expand_scale_gelu_kernel(const bf16* __restrict__ c, const float* __restrict_
         const float2 v = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(c + off)));
         *reinterpret_cast<uint32_t*>(tokens + off) = pack_bf16x2(gelu_erf(v.x * s0), gelu_erf(v.y * s1));
     }
+}
+
+// ====================================================================== IO plumbing
+__global__ void set_io_kernel(IoBlock* io, const void* images, void* final_out, void* tokens_out) {
+    io->images = images;
+    io->final_out = final_out;
+    io->tokens_out = tokens_out;
+}
+// tokens (workspace) -> caller buffer, 16 B per thread-iteration
+__global__ void __launch_bounds__(256)
+copy_tokens_kernel(const uint4* __restrict__ src, const IoBlock* __restrict__ io, size_t n16) {
+    uint4* __restrict__ dst = reinterpret_cast<uint4*>(io->tokens_out);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
 }  // namespace fvhd

@@ -88,6 +88,22 @@ def test_gemm_against_fp32(dev, M, N, K, act, use_bias, use_res):
     assert (D.float() - ref).abs().max().item() < 0.05 * max(1.0, ref.abs().max().item())
 
 
+def test_gemm_gelu_epilogue_wide_range(dev):
+    """The epilogue GELU (1-MUFU tanh form fitted to erf) must hold for pre-activations far outside +-8."""
+    eng = pkg.Engine(64, 0, 2, 1)
+    g = torch.Generator().manual_seed(9)
+    M, N, K = 512, 256, 128
+    A = (torch.randn(M, K, generator=g) * 8).to(torch.bfloat16).to(dev)
+    W = (torch.randn(N, K, generator=g)).to(torch.bfloat16).to(dev)       # pre-activations ~ N(0, 90^2)
+    D = eng.gemm(A, W, None, None, 1)
+    pre = A.float() @ W.float().t()
+    ref = torch.nn.functional.gelu(pre)
+    assert pre.abs().max().item() > 200
+    assert rel_l2(D.float(), ref) < 4e-3
+    small = pre.abs() < 6                                                  # the non-saturated region, absolute check
+    assert (D.float() - ref)[small].abs().max().item() < 0.03
+
+
 def test_gemm_linearity_large(dev):
     """Size-independent property at a bench-size problem: D(A1 + A2) == D(A1) + D(A2) (no bias)."""
     eng = pkg.Engine(64, 0, 2, 1)

@@ -55,6 +55,19 @@ def main():
             P(f"gemm M={M} N={N} K={K}: EXC {e}")
             raise
 
+    # determinism / race probe: same GEMM 20x, count distinct results
+    for (M, N, K) in [(256, 384, 384), (256, 1536, 384), (256, 384, 1536), (64, 768, 768), (1024, 192, 768), (4096, 1536, 384)]:
+        A = torch.randn(M, K, generator=g).to(torch.bfloat16).to(dev)
+        W = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(dev)
+        b = torch.randn(N, generator=g).to(dev)
+        ref = torch.nn.functional.gelu(A.float() @ W.float().t() + b)
+        errs = []
+        for _ in range(20):
+            D = eng0.gemm(A, W, b, None, 1)
+            errs.append(rel(D.float(), ref))
+        torch.cuda.synchronize()
+        P(f"repeat gemm M={M} N={N} K={K}: min {min(errs):.3e} max {max(errs):.3e} bad {sum(e > 5e-3 for e in errs)}/20")
+
     sd = fx.tower_state_dict()
     psd = fx.projector_state_dict(896)
     x = fx.synthetic_images(1, R)
