@@ -121,6 +121,10 @@ int fvhd_profile_steps(fvhd_handle h, void* stream, const void* images, int img_
 /* Number of kernel launches one forward of `batch` images enqueues. */
 int fvhd_launches_per_forward(fvhd_handle h, int batch);
 
+/* Debug: subsequent fvhd_gemm calls write 16 globaltimer stamps per CTA into `dev_buf` (NULL = off), optionally with a
+ * forced N tile (0 = cost model) and a cluster-size cap (1/2/4).  Process-global; not for production use. */
+int fvhd_debug_gemm_trace(void* dev_buf_16_u64_per_cta, int force_bn, int max_cs);
+
 /* Stand-alone GEMM entry (tests): D[M,N] = act(A[M,K] W[N,K]^T + bias) + residual, bf16. */
 int fvhd_gemm(fvhd_handle h, void* stream, const void* A, const void* W, const void* bias, const void* residual,
               void* D, int M, int N, int K, int act);

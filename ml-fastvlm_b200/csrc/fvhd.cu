@@ -250,6 +250,43 @@ Buffers carve(fvhd_handle h, int batch) {
     return b;
 }
 
+// ------------------------------------------------------------------ launches
+// All kernels go through cudaLaunchKernelEx with programmatic stream serialization (PDL): a kernel may begin its
+// prologue while the previous one drains; the kernels themselves order their global accesses with pdl_wait().
+bool g_use_pdl = true;
+int g_gemm_max_cs = 4;
+unsigned long long* g_gemm_trace = nullptr;   // fvhd_debug_gemm_trace: device buffer, 16 stamps per CTA
+int g_force_bn = 0;                            // fvhd_debug_gemm_trace: force the N tile (0 = cost model)       // FVHD_GEMM_CS=1|2|4 caps the GEMM cluster size (1 = no multicast)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kc(int cluster, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (g_use_pdl) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = (unsigned)cluster;
+        at[n].val.clusterDim.y = 1;
+        at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    return launch_kc(1, kernel, grid, block, smem, st, args...);
+}
+
 // ------------------------------------------------------------------ CUDA lazy init
 template <typename K> cudaError_t set_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -269,8 +306,11 @@ int ensure_cuda(fvhd_handle h) {
     h->encode = reinterpret_cast<EncodeTiledFn>(fn);
     h->num_sms = prop.multiProcessorCount;
     { const char* e = getenv("FVHD_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
+    { const char* e = getenv("FVHD_NO_PDL"); g_use_pdl = !(e && e[0] == '1'); }
+    { const char* e = getenv("FVHD_GEMM_CS"); if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) g_gemm_max_cs = e[0] - '0'; }
     CUDA_TRY(h, set_smem(gemm_bf16_tcgen05_kernel, 227 * 1024));
-    CUDA_TRY(h, set_smem(repmixer_dw_kernel, MixCfg::SMEM));
+    CUDA_TRY(h, set_smem(repmixer_dw_kernel<16, 16, 256>, MixCfgT<16, 16>::SMEM));
+    CUDA_TRY(h, set_smem(repmixer_dw_kernel<8, 16, 128>, MixCfgT<8, 16>::SMEM));
     CUDA_TRY(h, set_smem(dwconv_kernel<7, 1, 1, 0, 16, 16, 8>, DwCfg<7, 1, 1, 16, 16>::SMEM));
     CUDA_TRY(h, set_smem(dwconv_kernel<7, 2, 2, 1, 8, 8, 4>, DwCfg<7, 2, 2, 8, 8>::SMEM));
     CUDA_TRY(h, set_smem(dwconv_kernel<3, 1, 2, 0, 16, 16, 8>, DwCfg<3, 1, 2, 16, 16>::SMEM));
@@ -283,11 +323,11 @@ int ensure_cuda(fvhd_handle h) {
 }
 
 // bf16 row-major [rows, K] matrix with row pitch `ld` elements -> 2-D tensor map, box {64, box_rows}, 128-B swizzle.
-int make_tmap(fvhd_handle h, CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+int make_tmap(fvhd_handle h, CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows, int box_cols = GEMM_BK) {
     if (((uintptr_t)ptr & 15) || (ld * 2) % 16) return fail(h, FVHD_ERR_INVALID, "TMA operand must be 16-B aligned (ptr %p, ld %lld)", ptr, (long long)ld);
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -297,60 +337,127 @@ int make_tmap(fvhd_handle h, CUtensorMap* m, const void* ptr, int64_t rows, int6
     return FVHD_OK;
 }
 
-// Tile-shape heuristic: minimise waves x (BN + fixed per-tile cost), prefer the larger tile on ties.
-int pick_bn(int M, int N, int num_sms) {
+// NHWC bf16 activation [B, H, W, C] -> 4-D tensor map, box {32 channels, box_w, box_h, 1}, no swizzle, zero OOB fill.
+int make_tmap_nhwc(fvhd_handle h, CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int box_w, int box_h) {
+    if ((uintptr_t)ptr & 15) return fail(h, FVHD_ERR_INVALID, "TMA operand must be 16-B aligned (ptr %p)", ptr);
+    if (box_w > 256 || box_h > 256) return fail(h, FVHD_ERR_INVALID, "TMA box %dx%d too large", box_w, box_h);
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)DW_CG, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, FVHD_ERR_CUDA, "cuTensorMapEncodeTiled(4D) failed (%d) B=%d H=%d W=%d C=%d box=%dx%d", (int)r, B, H, W, C, box_w, box_h);
+    return FVHD_OK;
+}
+
+// GEMM configuration = (BN, cluster size CS, which operand the cluster shares).  Cost model per CTA tile (cycles):
+//   load = num_kb * bytes_per_kblock / 36 B/clk   (gemm_trace: ~70 GB/s per SM while all SMs pull, ~10 TB/s chip-wide)
+//   mma  = num_kb * 4 * (128 * BN / 256)          (tcgen05 M=128: 128*N/256 cycles per K=16 instruction)
+//   epi  = 128 * BN * (GELU ? 10 : 6) / 256       (8 epilogue warps)
+//   tile = max(load, mma, epi) + 400 ;  total = rounds * tile, rounds = ceil(cluster_tiles / resident_clusters)
+struct GemmCfg { int bn, cs, share_b; long cost; };
+GemmCfg pick_gemm_cfg(int M, int N, int K, int act, int num_sms) {
     const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+    const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
     const int cands[5] = {256, 128, 96, 64, 32};
-    int best = 128;
-    long best_cost = -1;
+    GemmCfg best{128, 1, 0, -1};
     for (int bn : cands) {
         if (bn == 96 && N % 96) continue;               // 96 only when it divides N (C = 96 / 192 / 384 layers)
         if (bn == 256 && N % 256) continue;
         if (bn > 32 && bn > ((N + 31) / 32) * 32) continue;
-        const long tiles = (long)tiles_m * ((N + bn - 1) / bn);
-        const long waves = (tiles + num_sms - 1) / num_sms;
-        const long cost = waves * (bn + 24);
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+        const int tiles_n = (N + bn - 1) / bn;
+        for (int cs = 1; cs <= g_gemm_max_cs; cs *= 2) {
+            for (int share_b = 0; share_b < (cs == 1 ? 1 : 2); ++share_b) {
+                if (cs > 1 && share_b && (bn / cs) % 8) continue;          // slice boxes stay whole swizzle atoms
+                if (cs > 1 && share_b && tiles_m < cs) continue;
+                if (cs > 1 && !share_b && tiles_n < cs) continue;
+                const long ctiles = share_b ? (long)((tiles_m + cs - 1) / cs) * tiles_n : (long)tiles_m * ((tiles_n + cs - 1) / cs);
+                const long resident = cs == 4 ? (num_sms / 4) - 1 : num_sms / cs;   // GPC granularity costs ~1 cluster of 4
+                const long rounds = (ctiles + resident - 1) / resident;
+                const long bytes_kb = cs == 1 ? 16384 + bn * 128 : (share_b ? 16384 + bn * 128 / cs : 16384 / cs + bn * 128);
+                const long load = (long)num_kb * bytes_kb / 36;
+                const long mma = (long)num_kb * 4 * (128 * bn / 256);
+                const long epi = 128L * bn * (act ? 10 : 6) / 256;
+                long tile = load > mma ? load : mma;
+                if (epi > tile) tile = epi;
+                const long cost = rounds * (tile + 400);
+                if (best.cost < 0 || cost < best.cost) best = GemmCfg{bn, cs, share_b, cost};
+            }
+        }
     }
     return best;
 }
 
-// Build one GEMM launch step.  D may be nullptr => taken from RunCtx.final_out at launch time.
+// Build one GEMM launch step.  D may be nullptr => taken from the IoBlock at run time.
 int make_gemm_step(fvhd_handle h, Step* out, const IoBlock* io, const bf16* A, int lda, const bf16* W, const float* bias, const bf16* residual, int ldr,
                    bf16* D, int ldd, int M, int N, int K, int act) {
     if (N % 8 || K % 8) return fail(h, FVHD_ERR_INVALID, "GEMM N (%d) and K (%d) must be multiples of 8", N, K);
+    GemmCfg c = pick_gemm_cfg(M, N, K, act, h->num_sms);
+    if (g_force_bn) { c.bn = g_force_bn; c.cs = 1; c.share_b = 0; }
     GemmParams p{};
     p.M = M; p.N = N; p.K = K;
-    p.BN = pick_bn(M, N, h->num_sms);
+    p.BN = c.bn; p.cs = c.cs; p.share_b = c.share_b;
     const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
     p.stages = gemm_pick_stages(p.BN, num_kb);
     p.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
     p.tiles_n = (N + p.BN - 1) / p.BN;
+    p.ctiles = p.share_b ? ((p.tiles_m + p.cs - 1) / p.cs) * p.tiles_n : p.tiles_m * ((p.tiles_n + p.cs - 1) / p.cs);
+    p.trace = g_gemm_trace;
     p.D = D; p.io = io; p.ldd = ldd; p.bias = bias; p.residual = residual; p.ldr = ldr; p.act = act;
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, td;
     int rc;
-    if ((rc = make_tmap(h, &ta, A, M, K, lda, GEMM_BM)) != FVHD_OK) return rc;
-    if ((rc = make_tmap(h, &tb, W, N, K, K, p.BN)) != FVHD_OK) return rc;
-    const int tiles = p.tiles_m * p.tiles_n;
-    const dim3 grid(tiles < h->num_sms ? tiles : h->num_sms);
+    const int a_box = (p.cs > 1 && !p.share_b) ? GEMM_BM / p.cs : GEMM_BM;     // shared operand: each CTA loads a 1/CS slice
+    const int b_box = (p.cs > 1 && p.share_b) ? p.BN / p.cs : p.BN;
+    if ((rc = make_tmap(h, &ta, A, M, K, lda, a_box)) != FVHD_OK) return rc;
+    if ((rc = make_tmap(h, &tb, W, N, K, K, b_box)) != FVHD_OK) return rc;
+    // D leaves through TMA stores (box 64 cols x 32 rows, 128-B swizzle) when it is library memory known at plan time
+    p.tma_store = (D != nullptr && p.BN >= 64) ? 1 : 0;
+    if (p.tma_store) {
+        if ((rc = make_tmap(h, &td, D, M, N, ldd, 32, 64)) != FVHD_OK) return rc;
+    } else {
+        td = ta;
+    }
     const size_t smem = gemm_smem_bytes(p.BN, p.stages);
+    int resident = h->num_sms / p.cs;
+    if (p.cs > 1) {     // how many clusters of this shape can be co-resident (GPC granularity)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(h->num_sms / p.cs * p.cs));
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)p.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nc = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, gemm_bf16_tcgen05_kernel, &cfg);
+        if (e != cudaSuccess || nc < 1) return fail(h, FVHD_ERR_CUDA, "cudaOccupancyMaxActiveClusters(cs=%d): %s (%d)", p.cs, cudaGetErrorString(e), nc);
+        resident = nc;
+    }
+    const int nclusters = p.ctiles < resident ? p.ctiles : resident;
+    const dim3 grid((unsigned)(nclusters * p.cs));
+    const int cs = p.cs;
     *out = [=](cudaStream_t s, const RunCtx&) -> cudaError_t {
-        gemm_bf16_tcgen05_kernel<<<grid, GEMM_THREADS, smem, s>>>(ta, tb, p);
-        return cudaGetLastError();
+        return launch_kc(cs, gemm_bf16_tcgen05_kernel, grid, dim3(GEMM_THREADS), smem, s, ta, tb, td, p);
     };
     return FVHD_OK;
 }
 
 template <int KS, int S, int MULT, int ACT, int TOH, int TOW, int SW>
-Step make_dw_step(const bf16* in, bf16* out, const float* w, const float* b, int batch, int H, int W, int C) {
+int make_dw_step(fvhd_handle h, Step* out_step, const bf16* in, bf16* out, const float* w, const float* b, int batch, int H, int W, int C) {
+    using Cfg = DwCfg<KS, S, MULT, TOH, TOW>;
     const int Ho = (H + 2 * (KS / 2) - KS) / S + 1, Wo = (W + 2 * (KS / 2) - KS) / S + 1;
     const int tx = (Wo + TOW - 1) / TOW, ty = (Ho + TOH - 1) / TOH;
     const dim3 grid(tx * ty, C / DW_CG, batch);
-    const size_t smem = DwCfg<KS, S, MULT, TOH, TOW>::SMEM;
-    return [=](cudaStream_t s, const RunCtx&) -> cudaError_t {
-        dwconv_kernel<KS, S, MULT, ACT, TOH, TOW, SW><<<grid, DW_THREADS, smem, s>>>(in, out, w, b, H, W, C, Ho, Wo, tx);
-        return cudaGetLastError();
+    const size_t smem = Cfg::SMEM;
+    CUtensorMap tm;
+    int rc = make_tmap_nhwc(h, &tm, in, batch, H, W, C, Cfg::IWP, Cfg::IH);
+    if (rc != FVHD_OK) return rc;
+    *out_step = [=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+        return launch_k(dwconv_kernel<KS, S, MULT, ACT, TOH, TOW, SW>, grid, dim3(DW_THREADS), smem, s, tm, out, w, b, H, W, C, Ho, Wo, tx);
     };
+    return FVHD_OK;
 }
 
 const float* WF(fvhd_handle h, const std::string& n) { return reinterpret_cast<const float*>(h->wptr.at(n)); }
@@ -403,10 +510,9 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
             const dim3 grid(tiles * tiles, 1, batch);
             bf16* t0 = bf.T1;
             pl.add([=](cudaStream_t s, const RunCtx& ctx) -> cudaError_t {
-                if (ctx.img_dtype == FVHD_F32) stem_kernel<float><<<grid, STEM_THREADS, STEM_SMEM, s>>>(io, t0, w0, b0, w1, b1, R, tiles);
-                else if (ctx.img_dtype == FVHD_F16) stem_kernel<__half><<<grid, STEM_THREADS, STEM_SMEM, s>>>(io, t0, w0, b0, w1, b1, R, tiles);
-                else stem_kernel<bf16><<<grid, STEM_THREADS, STEM_SMEM, s>>>(io, t0, w0, b0, w1, b1, R, tiles);
-                return cudaGetLastError();
+                if (ctx.img_dtype == FVHD_F32) return launch_k(stem_kernel<float>, grid, dim3(STEM_THREADS), STEM_SMEM, s, io, t0, w0, b0, w1, b1, R, tiles);
+                if (ctx.img_dtype == FVHD_F16) return launch_k(stem_kernel<__half>, grid, dim3(STEM_THREADS), STEM_SMEM, s, io, t0, w0, b0, w1, b1, R, tiles);
+                return launch_k(stem_kernel<bf16>, grid, dim3(STEM_THREADS), STEM_SMEM, s, io, t0, w0, b0, w1, b1, R, tiles);
             }, "stem_kernel", U, 2.0 * batch * ((double)(R / 2) * (R / 2) * 96 * 27 + (double)(R / 4) * (R / 4) * 96 * 9),
                (double)batch * (3.0 * R * R * 2 + (double)(R / 4) * (R / 4) * 96 * 2));
             if ((rc = add_gemm(h, pl, U, t0, 96, WB(h, "stem.w2"), WF(h, "stem.b2"), nullptr, 0, out, 96, M, 96, 96, 1)) != FVHD_OK) return rc;
@@ -415,25 +521,30 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
         }
         case 1: {   // RepMixerBlock: fused dw3x3 -> y, dw7x7(+BN) -> z ; fc1+GELU ; fc2 (+layer scale folded) + y
             const float *w3 = WF(h, p + "mix.w"), *b3 = WF(h, p + "mix.b"), *w7 = WF(h, p + "dw.w"), *b7 = WF(h, p + "dw.b");
-            const int tx = (W + MixCfg::TO - 1) / MixCfg::TO, ty = (H + MixCfg::TO - 1) / MixCfg::TO;
+            // tile choice: 16x16 (256 thr) unless that leaves fewer than ~2 CTAs per SM -> 8x16 (128 thr, 4 CTAs/SM)
+            const long ctas16 = (long)((W + 15) / 16) * ((H + 15) / 16) * (c / DW_CG) * batch;
+            const bool small = ctas16 < 2L * h->num_sms;
+            const int TH = small ? 8 : 16;
+            const int tx = (W + 15) / 16, ty = (H + TH - 1) / TH;
             const dim3 grid(tx * ty, c / DW_CG, batch);
             bf16 *y = bf.Y, *z = bf.Z;
+            CUtensorMap tmx;
+            if ((rc = make_tmap_nhwc(h, &tmx, in, batch, H, W, c, small ? MixCfgT<8, 16>::XP : MixCfgT<16, 16>::XP,
+                                     small ? MixCfgT<8, 16>::XH : MixCfgT<16, 16>::XH)) != FVHD_OK) return rc;
             pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
-                repmixer_dw_kernel<<<grid, DW_THREADS, MixCfg::SMEM, s>>>(in, y, z, w3, b3, w7, b7, H, W, c, tx);
-                return cudaGetLastError();
+                if (small) return launch_k(repmixer_dw_kernel<8, 16, 128>, grid, dim3(128), MixCfgT<8, 16>::SMEM, s, tmx, y, z, w3, b3, w7, b7, H, W, c, tx);
+                return launch_k(repmixer_dw_kernel<16, 16, 256>, grid, dim3(256), MixCfgT<16, 16>::SMEM, s, tmx, y, z, w3, b3, w7, b7, H, W, c, tx);
             }, "repmixer_dw_kernel", U, 2.0 * Md * c * 58, 3.0 * Md * c * 2);
             if ((rc = add_convffn_steps(h, pl, U, p, bf, z, y, out, M, c)) != FVHD_OK) return rc;
             break;
         }
         case 2: {   // PatchEmbed: dw7x7 s2 (x2 channels) + GELU ; 1x1 + GELU
-            pl.add(make_dw_step<7, 2, 2, 1, 8, 8, 4>(in, bf.T1, WF(h, p + "dw.w"), WF(h, p + "dw.b"), batch, H, W, c), "dwconv_kernel<7,2,2>", U,
-                   2.0 * Md * u.cout * 49, 2.0 * ((double)batch * u.in_elems + Md * u.cout));
+            { Step ds; if ((rc = make_dw_step<7, 2, 2, 1, 8, 8, 4>(h, &ds, in, bf.T1, WF(h, p + "dw.w"), WF(h, p + "dw.b"), batch, H, W, c)) != FVHD_OK) return rc; pl.add(ds, "dwconv_kernel<7,2,2>", U, 2.0 * Md * u.cout * 49, 2.0 * ((double)batch * u.in_elems + Md * u.cout)); }
             if ((rc = add_gemm(h, pl, U, bf.T1, u.cout, WB(h, p + "pw.w"), WF(h, p + "pw.b"), nullptr, 0, out, u.cout, M, u.cout, u.cout, 1)) != FVHD_OK) return rc;
             break;
         }
         case 3:     // RepCPE: dw7x7 + bias (identity folded into the centre tap)
-            pl.add(make_dw_step<7, 1, 1, 0, 16, 16, 8>(in, out, WF(h, p + "dw.w"), WF(h, p + "dw.b"), batch, H, W, c), "dwconv_kernel<7,1,1>", U,
-                   2.0 * Md * c * 49, 4.0 * Md * c);
+            { Step ds; if ((rc = make_dw_step<7, 1, 1, 0, 16, 16, 8>(h, &ds, in, out, WF(h, p + "dw.w"), WF(h, p + "dw.b"), batch, H, W, c)) != FVHD_OK) return rc; pl.add(ds, "dwconv_kernel<7,1,1>", U, 2.0 * Md * c * 49, 4.0 * Md * c); }
             break;
         case 4: {   // AttentionBlock
             const int N = H * W;
@@ -442,43 +553,36 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
             const int lngrid = (M + 7) / 8;
             if (c != 768 && c != 1536) return fail(h, FVHD_ERR_INVALID, "LayerNorm kernel expects C in {768,1536}, got %d", c);
             pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
-                if (c == 768) layernorm_channel_kernel<3><<<lngrid, 256, 0, s>>>(in, t1, lw, lb, M, 1e-5f);
-                else layernorm_channel_kernel<6><<<lngrid, 256, 0, s>>>(in, t1, lw, lb, M, 1e-5f);
-                return cudaGetLastError();
+                if (c == 768) return launch_k(layernorm_channel_kernel<3>, dim3(lngrid), dim3(256), 0, s, in, t1, lw, lb, M, 1e-5f);
+                return launch_k(layernorm_channel_kernel<6>, dim3(lngrid), dim3(256), 0, s, in, t1, lw, lb, M, 1e-5f);
             }, "layernorm_channel_kernel", U, 0.0, 4.0 * Md * c);
             if ((rc = add_gemm(h, pl, U, t1, c, WB(h, p + "qkv.w"), nullptr, nullptr, 0, qkv, 3 * c, M, 3 * c, c, 0)) != FVHD_OK) return rc;
             const dim3 agrid((N + 63) / 64, c / 32, batch);
             const float sl2 = 0.17677669529663687f * 1.4426950408889634f;   // 32^-0.5 * log2(e)
             pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
-                attention_kernel<<<agrid, 128, 0, s>>>(qkv, t1, N, c, sl2);
-                return cudaGetLastError();
+                return launch_k(attention_kernel, agrid, dim3(128), 0, s, qkv, t1, N, c, sl2);
             }, "attention_kernel", U, 4.0 * batch * (double)N * N * c, 8.0 * Md * c);
             if ((rc = add_gemm(h, pl, U, t1, c, WB(h, p + "proj.w"), WF(h, p + "proj.b"), in, c, x1, c, M, c, c, 0)) != FVHD_OK) return rc;
-            pl.add(make_dw_step<7, 1, 1, 0, 16, 16, 8>(x1, bf.Z, WF(h, p + "dw.w"), WF(h, p + "dw.b"), batch, H, W, c), "dwconv_kernel<7,1,1>", U,
-                   2.0 * Md * c * 49, 4.0 * Md * c);
+            { Step ds; if ((rc = make_dw_step<7, 1, 1, 0, 16, 16, 8>(h, &ds, x1, bf.Z, WF(h, p + "dw.w"), WF(h, p + "dw.b"), batch, H, W, c)) != FVHD_OK) return rc; pl.add(ds, "dwconv_kernel<7,1,1>", U, 2.0 * Md * c * 49, 4.0 * Md * c); }
             if ((rc = add_convffn_steps(h, pl, U, p, bf, bf.Z, x1, out, M, c)) != FVHD_OK) return rc;
             break;
         }
         case 5: {   // conv_exp: dw3x3 (x2 channels) -> SE -> GELU -> tokens
             const int HW = H * W;
             bf16* cexp = bf.T1;
-            pl.add(make_dw_step<3, 1, 2, 0, 16, 16, 8>(in, cexp, WF(h, p + "dw.w"), WF(h, p + "dw.b"), batch, H, W, c), "dwconv_kernel<3,1,2>", U,
-                   2.0 * Md * 3072 * 9, 2.0 * Md * (1536 + 3072));
+            { Step ds; if ((rc = make_dw_step<3, 1, 2, 0, 16, 16, 8>(h, &ds, in, cexp, WF(h, p + "dw.w"), WF(h, p + "dw.b"), batch, H, W, c)) != FVHD_OK) return rc; pl.add(ds, "dwconv_kernel<3,1,2>", U, 2.0 * Md * 3072 * 9, 2.0 * Md * (1536 + 3072)); }
             float *pooled = bf.pooled, *sr = bf.sr;
             const bf16 *wr = WB(h, p + "se.r.w"), *we = WB(h, p + "se.e.w");
             const float *br = WF(h, p + "se.r.b"), *be = WF(h, p + "se.e.b");
             bf16* dst = last ? nullptr : out;
             pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
-                se_pool_kernel<<<dim3(3072 / 64, batch), 256, 0, s>>>(cexp, pooled, HW, 3072);
-                return cudaGetLastError();
+                return launch_k(se_pool_kernel, dim3(3072 / 64, batch), dim3(256), 0, s, cexp, pooled, HW, 3072);
             }, "se_pool_kernel", U, 0.0, 2.0 * Md * 3072);
             pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
-                se_reduce_kernel<<<dim3(kSeRd / 8, batch), 256, 0, s>>>(pooled, wr, br, sr, 3072, kSeRd);
-                return cudaGetLastError();
+                return launch_k(se_reduce_kernel, dim3(kSeRd / 8, batch), dim3(256), 0, s, pooled, wr, br, sr, 3072, kSeRd);
             }, "se_reduce_kernel", U, 2.0 * batch * 3072 * kSeRd, 2.0 * 3072 * kSeRd);
             pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
-                se_expand_scale_gelu_kernel<<<dim3(3072 / 128, batch), 256, 0, s>>>(cexp, sr, we, be, dst, io, HW, 3072, kSeRd);
-                return cudaGetLastError();
+                return launch_k(se_expand_scale_gelu_kernel, dim3(3072 / 128, batch), dim3(256), 0, s, cexp, sr, we, be, dst, io, HW, 3072, kSeRd);
             }, "se_expand_scale_gelu_kernel", U, 2.0 * batch * 3072 * kSeRd, 4.0 * Md * 3072 + 2.0 * 3072 * kSeRd);
             break;
         }
@@ -538,8 +642,7 @@ int run_steps(fvhd_handle h, Plan& pl, int s0, int s1, cudaStream_t st, const Ru
 }
 
 int set_io(fvhd_handle h, Plan& pl, cudaStream_t st, const void* images, void* final_out, void* tokens_out) {
-    set_io_kernel<<<1, 1, 0, st>>>(pl.io, images, final_out, tokens_out);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_k(set_io_kernel, dim3(1), dim3(1), 0, st, pl.io, images, final_out, tokens_out);
     if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "set_io_kernel launch failed: %s", cudaGetErrorString(e));
     return FVHD_OK;
 }
@@ -548,8 +651,7 @@ int launch_copy_tokens(fvhd_handle h, Plan& pl, cudaStream_t st, const bf16* src
     const size_t n16 = bytes / 16;
     int blocks = (int)((n16 + 255) / 256);
     if (blocks > 1184) blocks = 1184;
-    copy_tokens_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(src), pl.io, n16);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_k(copy_tokens_kernel, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const uint4*>(src), pl.io, n16);
     if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "copy_tokens_kernel launch failed: %s", cudaGetErrorString(e));
     return FVHD_OK;
 }
@@ -872,6 +974,13 @@ int fvhd_profile_steps(fvhd_handle h, void* stream, const void* images, int img_
     CUDA_TRY(h, cudaStreamSynchronize(st));
     for (int i = 0; i < n; ++i) CUDA_TRY(h, cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
     for (auto& e : ev) cudaEventDestroy(e);
+    return FVHD_OK;
+}
+
+int fvhd_debug_gemm_trace(void* dev_buf_16_u64_per_cta, int force_bn, int max_cs) {
+    g_gemm_trace = reinterpret_cast<unsigned long long*>(dev_buf_16_u64_per_cta);
+    g_force_bn = force_bn;
+    if (max_cs == 1 || max_cs == 2 || max_cs == 4) g_gemm_max_cs = max_cs;
     return FVHD_OK;
 }
 

@@ -37,7 +37,7 @@ stem_kernel(const IoBlock* __restrict__ io, bf16* __restrict__ out, const float*
     float* sin = b1s + STEM_C;                                           // [3][35][36]
     uint32_t* s1 = reinterpret_cast<uint32_t*>(sin + 3 * STEM_IN * STEM_INP);   // [289][49]
 
-    const T* __restrict__ img = reinterpret_cast<const T*>(io->images);
+    pdl_launch_dependents();
     const int b = blockIdx.z;
     const int ty0 = (blockIdx.x / tiles_x) * STEM_TO, tx0 = (blockIdx.x % tiles_x) * STEM_TO;
     const int R2 = R / 2, R4 = R / 4;
@@ -47,6 +47,8 @@ stem_kernel(const IoBlock* __restrict__ io, bf16* __restrict__ out, const float*
     for (int i = threadIdx.x; i < 27 * STEM_C; i += STEM_THREADS) w0s[i] = __ldg(w0 + i);
     for (int i = threadIdx.x; i < 9 * STEM_C; i += STEM_THREADS) w1s[i] = __ldg(w1 + i);
     if (threadIdx.x < STEM_C) { b0s[threadIdx.x] = __ldg(b0 + threadIdx.x); b1s[threadIdx.x] = __ldg(b1 + threadIdx.x); }
+    pdl_wait();                                                          // io block is written by set_io_kernel
+    const T* __restrict__ img = reinterpret_cast<const T*>(io->images);
     for (int i = threadIdx.x; i < 3 * STEM_IN * STEM_IN; i += STEM_THREADS) {
         const int ci = i / (STEM_IN * STEM_IN);
         const int rem = i - ci * STEM_IN * STEM_IN;
@@ -124,6 +126,8 @@ __global__ void __launch_bounds__(256)
 layernorm_channel_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
                          const float* __restrict__ beta, int M, float eps) {
     constexpr int C = NV * 256;
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -190,6 +194,8 @@ __global__ void __launch_bounds__(128)
 attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int N, int C, float scale_log2e) {
     __shared__ __align__(16) bf16 Ks[2][ATT_KC * ATT_PITCH];
     __shared__ __align__(16) bf16 Vs[2][ATT_KC * ATT_PITCH];
+    pdl_launch_dependents();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int head = blockIdx.y, b = blockIdx.z;
@@ -318,6 +324,8 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int N, in
 __global__ void __launch_bounds__(256)
 se_pool_kernel(const bf16* __restrict__ c, float* __restrict__ pooled, int HW, int C) {
     __shared__ float red[8][64];
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y, c0 = blockIdx.x * 64;
     const int cp = threadIdx.x & 31, sl = threadIdx.x >> 5;
     float a0 = 0.f, a1 = 0.f;
@@ -338,6 +346,8 @@ se_pool_kernel(const bf16* __restrict__ c, float* __restrict__ pooled, int HW, i
 __global__ void __launch_bounds__(256)
 se_reduce_kernel(const float* __restrict__ pooled, const bf16* __restrict__ wr /*[RD][C]*/, const float* __restrict__ br,
                  float* __restrict__ r, int C, int RD) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y, j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (j >= RD) return;
     float a = 0.f;
@@ -356,6 +366,8 @@ se_reduce_kernel(const float* __restrict__ pooled, const bf16* __restrict__ wr /
 __global__ void __launch_bounds__(256)
 se_expand_scale_gelu_kernel(const bf16* __restrict__ c, const float* __restrict__ r, const bf16* __restrict__ we /*[C][RD]*/,
                             const float* __restrict__ be, bf16* __restrict__ tokens_or_null, const IoBlock* __restrict__ io, int HW, int C, int RD) {
+    pdl_launch_dependents();
+    pdl_wait();
     bf16* __restrict__ tokens = tokens_or_null ? tokens_or_null : reinterpret_cast<bf16*>(io->final_out);
     __shared__ float rs[256];
     __shared__ float ss[128];
@@ -384,6 +396,8 @@ se_expand_scale_gelu_kernel(const bf16* __restrict__ c, const float* __restrict_
 
 // ====================================================================== IO plumbing
 __global__ void set_io_kernel(IoBlock* io, const void* images, void* final_out, void* tokens_out) {
+    pdl_launch_dependents();
+    pdl_wait();                 // the previous forward's last kernels may still be reading the block
     io->images = images;
     io->final_out = final_out;
     io->tokens_out = tokens_out;
@@ -391,6 +405,8 @@ __global__ void set_io_kernel(IoBlock* io, const void* images, void* final_out, 
 // tokens (workspace) -> caller buffer, 16 B per thread-iteration
 __global__ void __launch_bounds__(256)
 copy_tokens_kernel(const uint4* __restrict__ src, const IoBlock* __restrict__ io, size_t n16) {
+    pdl_launch_dependents();
+    pdl_wait();
     uint4* __restrict__ dst = reinterpret_cast<uint4*>(io->tokens_out);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
