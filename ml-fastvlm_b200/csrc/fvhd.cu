@@ -523,7 +523,8 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
             const float *w3 = WF(h, p + "mix.w"), *b3 = WF(h, p + "mix.b"), *w7 = WF(h, p + "dw.w"), *b7 = WF(h, p + "dw.b");
             // tile choice: 16x16 (256 thr) unless that leaves fewer than ~2 CTAs per SM -> 8x16 (128 thr, 4 CTAs/SM)
             const long ctas16 = (long)((W + 15) / 16) * ((H + 15) / 16) * (c / DW_CG) * batch;
-            const bool small = ctas16 < 2L * h->num_sms;
+            bool small = ctas16 < 2L * h->num_sms;
+            { const char* e = getenv("FVHD_MIX_TILE"); if (e && e[0] == '8') small = true; else if (e && e[0] == '1') small = false; }
             const int TH = small ? 8 : 16;
             const int tx = (W + 15) / 16, ty = (H + TH - 1) / TH;
             const dim3 grid(tx * ty, c / DW_CG, batch);
