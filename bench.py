@@ -264,8 +264,12 @@ def run_gpu_arm(args):
         gk = kernels["gemm_bf16_tcgen05_kernel"]
         ach = gk["flops"] / gk["ms"] / 1e9           # TFLOP/s
         peak = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
+        traffic = None          # dram__bytes_read+write per GEMM launch from the committed ncu pass of this command (B=1 only)
+        tpath = os.path.join(ROOT, "profiles", "gemm_dram_traffic.json")
+        if B == 1 and os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("bytes_per_launch")
         roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
-                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": f"{peak_src} (burst bf16 GEMM)",
+                    "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": f"{peak_src} (burst bf16 GEMM)",
                     "launches_per_step": gk["launches"], "avg_launch_us": round(1e3 * gk["ms"] / gk["launches"], 2),
                     "algorithmic_flops_per_step": gk["flops"], "share_of_step": round(gk["ms"] / sum(ms), 4)}
         # whole-step view against both roofs: F = 488.5 GFLOP, B_act + W bytes
