@@ -261,14 +261,17 @@ def run_gpu_arm(args):
             ktab.append({"kernel": name, "launches": k["launches"], "ms": round(k["ms"], 4), "share": round(k["ms"] / sum(ms), 4),
                          "tflops": round(k["flops"] / k["ms"] / 1e9, 1) if k["ms"] > 0 else None,
                          "gbs": round(k["bytes"] / k["ms"] / 1e6, 1) if k["ms"] > 0 else None})
-        gk = kernels["gemm_bf16_tcgen05_kernel"]
+        # the tensor-pipe kernels: the tcgen05 GEMM and the fused ConvFFN (fc1 -> GELU -> fc2 in one kernel)
+        tc_names = [n for n in ("gemm_bf16_tcgen05_kernel", "mlp_fused_tcgen05_kernel") if n in kernels]
+        gk = {"launches": sum(kernels[n]["launches"] for n in tc_names), "ms": sum(kernels[n]["ms"] for n in tc_names),
+              "flops": sum(kernels[n]["flops"] for n in tc_names), "bytes": sum(kernels[n]["bytes"] for n in tc_names)}
         ach = gk["flops"] / gk["ms"] / 1e9           # TFLOP/s
         peak = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
         traffic = None          # dram__bytes_read+write per GEMM launch from the committed ncu pass of this command (B=1 only)
         tpath = os.path.join(ROOT, "profiles", "gemm_dram_traffic.json")
         if B == 1 and os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("bytes_per_launch")
-        roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
+        roofline = {"bound": "tensor", "kernel": " + ".join(tc_names), "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
                     "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": f"{peak_src} (burst bf16 GEMM)",
                     "launches_per_step": gk["launches"], "avg_launch_us": round(1e3 * gk["ms"] / gk["launches"], 2),
                     "algorithmic_flops_per_step": gk["flops"], "share_of_step": round(gk["ms"] / sum(ms), 4)}

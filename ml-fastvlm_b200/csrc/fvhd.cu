@@ -17,6 +17,7 @@
 #include "../../include/fastvithd_b200.h"
 #include "dwconv.cuh"
 #include "gemm_tcgen05.cuh"
+#include "mlp_fused.cuh"
 #include "stem_attn_se.cuh"
 
 using namespace fvhd;
@@ -254,9 +255,11 @@ Buffers carve(fvhd_handle h, int batch) {
 // All kernels go through cudaLaunchKernelEx with programmatic stream serialization (PDL): a kernel may begin its
 // prologue while the previous one drains; the kernels themselves order their global accesses with pdl_wait().
 bool g_use_pdl = true;
-int g_gemm_max_cs = 4;
+int g_gemm_max_cs = 1;        // FVHD_GEMM_CS=1|2|4 caps the GEMM cluster size.  Default 1: at batch 1 the delivered-bytes rate is
+                              // the limit and multicast only reduces L2 reads -- measured no gain (profiles/r01_f_summary.md)
+bool g_use_fused_mlp = true;  // FVHD_NO_FUSED_MLP=1: ConvFFN as two GEMM launches (reference path of the bit-exactness test)
 unsigned long long* g_gemm_trace = nullptr;   // fvhd_debug_gemm_trace: device buffer, 16 stamps per CTA
-int g_force_bn = 0;                            // fvhd_debug_gemm_trace: force the N tile (0 = cost model)       // FVHD_GEMM_CS=1|2|4 caps the GEMM cluster size (1 = no multicast)
+int g_force_bn = 0;                            // fvhd_debug_gemm_trace: force the N tile (0 = cost model)
 template <typename... KArgs, typename... Args>
 cudaError_t launch_kc(int cluster, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -307,8 +310,10 @@ int ensure_cuda(fvhd_handle h) {
     h->num_sms = prop.multiProcessorCount;
     { const char* e = getenv("FVHD_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
     { const char* e = getenv("FVHD_NO_PDL"); g_use_pdl = !(e && e[0] == '1'); }
+    { const char* e = getenv("FVHD_NO_FUSED_MLP"); g_use_fused_mlp = !(e && e[0] == '1'); }
     { const char* e = getenv("FVHD_GEMM_CS"); if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) g_gemm_max_cs = e[0] - '0'; }
     CUDA_TRY(h, set_smem(gemm_bf16_tcgen05_kernel, 227 * 1024));
+    CUDA_TRY(h, set_smem(mlp_fused_tcgen05_kernel, 227 * 1024));
     CUDA_TRY(h, set_smem(repmixer_dw_kernel<16, 16, 256>, MixCfgT<16, 16>::SMEM));
     CUDA_TRY(h, set_smem(repmixer_dw_kernel<8, 16, 128>, MixCfgT<8, 16>::SMEM));
     CUDA_TRY(h, set_smem(dwconv_kernel<7, 1, 1, 0, 16, 16, 8>, DwCfg<7, 1, 1, 16, 16>::SMEM));
@@ -482,6 +487,25 @@ int add_convffn_steps(fvhd_handle h, Plan& pl, int unit, const std::string& p, c
     return add_gemm(h, pl, unit, bf.H4, 4 * c, WB(h, p + "fc2.w"), WF(h, p + "fc2.b"), resid, c, out, c, M, c, 4 * c, 0);
 }
 
+// ConvFFN of a RepMixer block as ONE kernel (C in {96, 192}): hidden stays in TMEM / smem (mlp_fused.cuh).
+int add_fused_mlp_step(fvhd_handle h, Plan& pl, int unit, const std::string& p, const bf16* z, const bf16* resid, bf16* out, int M, int c) {
+    MlpParams mp{};
+    mp.M = M; mp.C = c; mp.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+    mp.b1 = WF(h, p + "fc1.b"); mp.b2 = WF(h, p + "fc2.b"); mp.resid = resid; mp.D = out;
+    CUtensorMap tz, tw1, tw2, td;
+    int rc;
+    if ((rc = make_tmap(h, &tz, z, M, c, c, GEMM_BM)) != FVHD_OK) return rc;
+    if ((rc = make_tmap(h, &tw1, WB(h, p + "fc1.w"), 4 * c, c, c, MLP_NH)) != FVHD_OK) return rc;
+    if ((rc = make_tmap(h, &tw2, WB(h, p + "fc2.w"), c, 4 * c, 4 * c, c)) != FVHD_OK) return rc;
+    if ((rc = make_tmap(h, &td, out, M, c, c, 32, 64)) != FVHD_OK) return rc;
+    const dim3 grid((unsigned)(mp.tiles_m < h->num_sms ? mp.tiles_m : h->num_sms));
+    const size_t smem = mlp_smem_bytes(c);
+    pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+        return launch_k(mlp_fused_tcgen05_kernel, grid, dim3(MLP_THREADS), smem, s, tz, tw1, tw2, td, mp);
+    }, "mlp_fused_tcgen05_kernel", unit, 2.0 * gemm_flops(M, 4 * c, c), 2.0 * (3.0 * M * c + 8.0 * c * c) + 20.0 * c);
+    return FVHD_OK;
+}
+
 int build_plan(fvhd_handle h, int batch, Plan& pl) {
     pl = Plan();
     pl.batch = batch;
@@ -536,7 +560,11 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
                 if (small) return launch_k(repmixer_dw_kernel<8, 16, 128>, grid, dim3(128), MixCfgT<8, 16>::SMEM, s, tmx, y, z, w3, b3, w7, b7, H, W, c, tx);
                 return launch_k(repmixer_dw_kernel<16, 16, 256>, grid, dim3(256), MixCfgT<16, 16>::SMEM, s, tmx, y, z, w3, b3, w7, b7, H, W, c, tx);
             }, "repmixer_dw_kernel", U, 2.0 * Md * c * 58, 3.0 * Md * c * 2);
-            if ((rc = add_convffn_steps(h, pl, U, p, bf, z, y, out, M, c)) != FVHD_OK) return rc;
+            if (g_use_fused_mlp && c <= 192) {
+                if ((rc = add_fused_mlp_step(h, pl, U, p, z, y, out, M, c)) != FVHD_OK) return rc;
+            } else {
+                if ((rc = add_convffn_steps(h, pl, U, p, bf, z, y, out, M, c)) != FVHD_OK) return rc;
+            }
             break;
         }
         case 2: {   // PatchEmbed: dw7x7 s2 (x2 channels) + GELU ; 1x1 + GELU
@@ -804,7 +832,7 @@ int fvhd_launches_per_forward(fvhd_handle h, int batch) {
     for (const UnitDesc& u : h->units) {
         switch (u.kind) {
         case 0: steps += 2; break;
-        case 1: steps += 3; break;
+        case 1: steps += (g_use_fused_mlp && u.cin <= 192) ? 2 : 3; break;
         case 2: steps += 2; break;
         case 3: steps += 1; break;
         case 4: steps += 7; break;

@@ -219,6 +219,29 @@ def test_missing_weights_and_workspace_fail_loudly(packed, dev):
         pkg.Engine(256, 0, 2, 1).forward(torch.rand(1, 3, 256, 256, device=dev))            # load() not called
 
 
+def test_fused_convffn_is_bit_identical_to_two_gemms(packed, dev):
+    """mlp_fused_tcgen05_kernel keeps the fc2 accumulation order of the unfused path (hidden chunk j == k-block j), so the
+    whole forward must agree BIT FOR BIT with FVHD_NO_FUSED_MLP=1 (evaluated in a subprocess: the switch is read once)."""
+    import subprocess, sys, tempfile
+    code = (
+        "import sys, torch; sys.path.insert(0, %r)\n"
+        "import ml_fastvlm_b200 as pkg; from oracle import fixture as fx\n"
+        "pk = pkg.pack_tower(fx.tower_state_dict()); pk.update(pkg.pack_projector(fx.projector_state_dict(896)))\n"
+        "eng = pkg.Engine(512, 896, 2, 2).load(pk, torch.device('cuda:0'))\n"
+        "t, p = eng.forward(fx.synthetic_images(2, 512, seed=4).to('cuda:0'), True, True)\n"
+        "torch.save({'t': t.cpu(), 'p': p.cpu(), 'launches': eng.launches_per_forward(2)}, sys.argv[1])\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    outs = []
+    for env_val in ("0", "1"):
+        f = tempfile.NamedTemporaryFile(suffix=".pt", delete=False).name
+        env = dict(os.environ, FVHD_NO_FUSED_MLP=env_val)
+        subprocess.run([sys.executable, "-c", code, f], check=True, env=env, timeout=300)
+        outs.append(torch.load(f))
+        os.unlink(f)
+    assert outs[0]["launches"] == outs[1]["launches"] - 14            # 2 + 12 RepMixer blocks lose one launch each
+    assert torch.isfinite(outs[0]["p"].float()).all()
+    assert torch.equal(outs[0]["t"], outs[1]["t"]) and torch.equal(outs[0]["p"], outs[1]["p"])
+
+
 # ------------------------------------------------------------------ drop-in modules
 class _Args:
     mm_vision_tower = "mobileclip_l_256"
