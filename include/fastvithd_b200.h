@@ -88,6 +88,13 @@ int fvhd_set_workspace(fvhd_handle h, void* dptr, size_t bytes);
 int fvhd_forward(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch,
                  void* tokens, void* projected);
 
+/* fvhd_forward whose FINAL output (projected tokens, or tower tokens for a projector-less plan) is written with
+ * `out_image_stride` ELEMENTS between consecutive images (0 = dense).  With projected = embeds + pos*H and
+ * out_image_stride = L*H the visual tokens land directly inside a [B, L, H] LLM input-embedding buffer: the token
+ * splice of prepare_inputs_labels_for_multimodal (llava_arch.py:251-271) becomes the projector's store, no copy. */
+int fvhd_forward_strided(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch,
+                         void* tokens, void* projected, long long out_image_stride);
+
 /* Same call with HOST buffers: H2D of the images, the forward, D2H of the result, one stream sync.
  * `host_out` receives `projected` when the plan has a projector, else `tokens` (bf16). */
 int fvhd_encode_images_host(fvhd_handle h, void* stream, const void* host_images, int img_dtype, int batch,

@@ -396,7 +396,7 @@ GemmCfg pick_gemm_cfg(int M, int N, int K, int act, int num_sms) {
 }
 
 // Build one GEMM launch step.  D may be nullptr => taken from the IoBlock at run time.
-int make_gemm_step(fvhd_handle h, Step* out, const IoBlock* io, const bf16* A, int lda, const bf16* W, const float* bias, const bf16* residual, int ldr,
+int make_gemm_step(fvhd_handle h, Step* out, const IoBlock* io, int rows_per_image, const bf16* A, int lda, const bf16* W, const float* bias, const bf16* residual, int ldr,
                    bf16* D, int ldd, int M, int N, int K, int act) {
     if (N % 8 || K % 8) return fail(h, FVHD_ERR_INVALID, "GEMM N (%d) and K (%d) must be multiples of 8", N, K);
     GemmCfg c = pick_gemm_cfg(M, N, K, act, h->num_sms);
@@ -410,7 +410,7 @@ int make_gemm_step(fvhd_handle h, Step* out, const IoBlock* io, const bf16* A, i
     p.tiles_n = (N + p.BN - 1) / p.BN;
     p.ctiles = p.share_b ? ((p.tiles_m + p.cs - 1) / p.cs) * p.tiles_n : p.tiles_m * ((p.tiles_n + p.cs - 1) / p.cs);
     p.trace = g_gemm_trace;
-    p.D = D; p.io = io; p.ldd = ldd; p.bias = bias; p.residual = residual; p.ldr = ldr; p.act = act;
+    p.D = D; p.io = io; p.rows_per_image = rows_per_image > 0 ? rows_per_image : 1; p.ldd = ldd; p.bias = bias; p.residual = residual; p.ldr = ldr; p.act = act;
     CUtensorMap ta, tb, td;
     int rc;
     const int a_box = (p.cs > 1 && !p.share_b) ? GEMM_BM / p.cs : GEMM_BM;     // shared operand: each CTA loads a 1/CS slice
@@ -475,7 +475,7 @@ double gemm_bytes(double M, double N, double K, bool res) { return 2.0 * (M * K 
 int add_gemm(fvhd_handle h, Plan& pl, int unit, const bf16* A, int lda, const bf16* W, const float* bias, const bf16* residual, int ldr,
              bf16* D, int ldd, int M, int N, int K, int act) {
     Step g;
-    int rc = make_gemm_step(h, &g, pl.io, A, lda, W, bias, residual, ldr, D, ldd, M, N, K, act);
+    int rc = make_gemm_step(h, &g, pl.io, h->ntok, A, lda, W, bias, residual, ldr, D, ldd, M, N, K, act);
     if (rc != FVHD_OK) return rc;
     pl.add(g, kGemm, unit, gemm_flops(M, N, K), gemm_bytes(M, N, K, residual != nullptr));
     return FVHD_OK;
@@ -670,8 +670,8 @@ int run_steps(fvhd_handle h, Plan& pl, int s0, int s1, cudaStream_t st, const Ru
     return FVHD_OK;
 }
 
-int set_io(fvhd_handle h, Plan& pl, cudaStream_t st, const void* images, void* final_out, void* tokens_out) {
-    cudaError_t e = launch_k(set_io_kernel, dim3(1), dim3(1), 0, st, pl.io, images, final_out, tokens_out);
+int set_io(fvhd_handle h, Plan& pl, cudaStream_t st, const void* images, void* final_out, void* tokens_out, long long final_image_stride) {
+    cudaError_t e = launch_k(set_io_kernel, dim3(1), dim3(1), 0, st, pl.io, images, final_out, tokens_out, final_image_stride);
     if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "set_io_kernel launch failed: %s", cudaGetErrorString(e));
     return FVHD_OK;
 }
@@ -845,6 +845,11 @@ int fvhd_launches_per_forward(fvhd_handle h, int batch) {
 }
 
 int fvhd_forward(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch, void* tokens, void* projected) {
+    return fvhd_forward_strided(h, stream, images, img_dtype, batch, tokens, projected, 0);
+}
+
+int fvhd_forward_strided(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch, void* tokens, void* projected,
+                         long long out_image_stride) {
     int rc = check_ready(h, batch);
     if (rc != FVHD_OK) return rc;
     if (!images) return fail(h, FVHD_ERR_INVALID, "images is null");
@@ -855,8 +860,14 @@ int fvhd_forward(fvhd_handle h, void* stream, const void* images, int img_dtype,
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const size_t img_stride = (size_t)3 * h->R * h->R * dtype_size(img_dtype);
     const size_t tok_stride = (size_t)h->ntok * FVHD_EMBED_DIM * 2;
-    const size_t prj_stride = (size_t)h->ntok * h->cfg.projector_hidden * 2;
     const int nunits = (int)h->units.size();
+    // final output (projected tokens, or tower tokens when the plan has no projector): dense, or `out_image_stride`
+    // elements between images (>= tokens-per-image * dim) when the destination is an LLM embedding buffer
+    const long long dense_final = (long long)h->ntok * (has_proj ? h->cfg.projector_hidden : FVHD_EMBED_DIM);
+    if (out_image_stride != 0 && out_image_stride < dense_final)
+        return fail(h, FVHD_ERR_INVALID, "out_image_stride %lld < tokens * dim = %lld", out_image_stride, dense_final);
+    const long long final_stride = out_image_stride ? out_image_stride : dense_final;
+    const size_t prj_stride = (size_t)final_stride * 2;
     const int tok_unit = has_proj ? nunits - 2 : nunits - 1;
     for (int b0 = 0; b0 < batch; b0 += h->cfg.max_batch) {
         const int bc = (batch - b0) < h->cfg.max_batch ? (batch - b0) : h->cfg.max_batch;
@@ -865,16 +876,16 @@ int fvhd_forward(fvhd_handle h, void* stream, const void* images, int img_dtype,
         RunCtx ctx;
         ctx.img_dtype = img_dtype;
         const void* img = reinterpret_cast<const uint8_t*>(images) + (size_t)b0 * img_stride;
-        uint8_t* tok_dst = tokens ? reinterpret_cast<uint8_t*>(tokens) + (size_t)b0 * tok_stride : nullptr;
+        uint8_t* tok_dst = tokens ? reinterpret_cast<uint8_t*>(tokens) + (size_t)b0 * (has_proj ? tok_stride : (size_t)final_stride * 2) : nullptr;
         uint8_t* prj_dst = projected ? reinterpret_cast<uint8_t*>(projected) + (size_t)b0 * prj_stride : nullptr;
         if (has_proj) {
             // tokens stay in the workspace (the projector's TMA map points there); copied out if requested
             const int last_unit = projected ? nunits - 1 : nunits - 2;
-            if ((rc = set_io(h, *pl, st, img, prj_dst, tok_dst)) != FVHD_OK) return rc;
+            if ((rc = set_io(h, *pl, st, img, prj_dst, tok_dst, final_stride)) != FVHD_OK) return rc;
             if ((rc = run_forward(h, *pl, st, ctx, pl->unit_steps[last_unit].second, tok_dst ? pl->unit_out[tok_unit] : nullptr,
                                   (size_t)bc * tok_stride)) != FVHD_OK) return rc;
         } else {
-            if ((rc = set_io(h, *pl, st, img, tok_dst, nullptr)) != FVHD_OK) return rc;
+            if ((rc = set_io(h, *pl, st, img, tok_dst, nullptr, final_stride)) != FVHD_OK) return rc;
             if ((rc = run_forward(h, *pl, st, ctx, (int)pl->steps.size(), nullptr, 0)) != FVHD_OK) return rc;
         }
     }
@@ -929,7 +940,7 @@ int fvhd_run_units(fvhd_handle h, void* stream, int first, int last, const void*
         CUDA_TRY(h, cudaMemcpyAsync(pl->unit_in[first], in, (size_t)batch * h->units[first].in_elems * 2, cudaMemcpyDeviceToDevice, st));
     const size_t out_bytes = (size_t)batch * h->units[last].out_elems * 2;
     // the last unit of the plan writes straight to the caller's buffer; earlier units are copied out of the workspace
-    if ((rc = set_io(h, *pl, st, in, last == nunits - 1 ? out : nullptr, nullptr)) != FVHD_OK) return rc;
+    if ((rc = set_io(h, *pl, st, in, last == nunits - 1 ? out : nullptr, nullptr, h->units[nunits - 1].out_elems)) != FVHD_OK) return rc;
     if ((rc = run_steps(h, *pl, pl->unit_steps[first].first, pl->unit_steps[last].second, st, ctx)) != FVHD_OK) return rc;
     if (last != nunits - 1) CUDA_TRY(h, cudaMemcpyAsync(out, pl->unit_out[last], out_bytes, cudaMemcpyDeviceToDevice, st));
     return FVHD_OK;
@@ -948,7 +959,7 @@ int fvhd_profile_units(fvhd_handle h, void* stream, const void* images, int img_
     for (auto& e : ev) CUDA_TRY(h, cudaEventCreate(&e));
     RunCtx ctx;
     ctx.img_dtype = img_dtype;
-    if ((rc = set_io(h, *pl, st, images, pl->unit_out[nunits - 1], nullptr)) != FVHD_OK) return rc;   // result stays in the workspace
+    if ((rc = set_io(h, *pl, st, images, pl->unit_out[nunits - 1], nullptr, h->units[nunits - 1].out_elems)) != FVHD_OK) return rc;   // result stays in the workspace
     CUDA_TRY(h, cudaEventRecord(ev[0], st));
     for (int u = 0; u < nunits; ++u) {
         if ((rc = run_steps(h, *pl, pl->unit_steps[u].first, pl->unit_steps[u].second, st, ctx)) != FVHD_OK) return rc;
@@ -994,7 +1005,7 @@ int fvhd_profile_steps(fvhd_handle h, void* stream, const void* images, int img_
     for (auto& e : ev) CUDA_TRY(h, cudaEventCreate(&e));
     RunCtx ctx;
     ctx.img_dtype = img_dtype;
-    if ((rc = set_io(h, *pl, st, images, pl->unit_out[h->units.size() - 1], nullptr)) != FVHD_OK) return rc;
+    if ((rc = set_io(h, *pl, st, images, pl->unit_out[h->units.size() - 1], nullptr, h->units[h->units.size() - 1].out_elems)) != FVHD_OK) return rc;
     CUDA_TRY(h, cudaEventRecord(ev[0], st));
     for (int i = 0; i < n; ++i) {
         if ((rc = run_steps(h, *pl, i, i + 1, st, ctx)) != FVHD_OK) return rc;
@@ -1018,7 +1029,7 @@ int fvhd_gemm(fvhd_handle h, void* stream, const void* A, const void* W, const v
     int rc = ensure_cuda(h);
     if (rc != FVHD_OK) return rc;
     Step s;
-    if ((rc = make_gemm_step(h, &s, nullptr, (const bf16*)A, K, (const bf16*)W, (const float*)bias, (const bf16*)residual, N, (bf16*)D, N, M, N, K, act)) != FVHD_OK) return rc;
+    if ((rc = make_gemm_step(h, &s, nullptr, 1, (const bf16*)A, K, (const bf16*)W, (const float*)bias, (const bf16*)residual, N, (bf16*)D, N, M, N, K, act)) != FVHD_OK) return rc;
     if (!D) return fail(h, FVHD_ERR_INVALID, "D is null");
     RunCtx ctx{};
     cudaError_t e = s(reinterpret_cast<cudaStream_t>(stream), ctx);

@@ -40,6 +40,7 @@ struct GemmParams {
     int tiles_m, tiles_n;
     bf16* D;           // [M, ldd] bf16; nullptr => io->final_out (caller memory)
     const IoBlock* io;
+    int rows_per_image;      // D == nullptr only: rows (tokens) per image, images io->final_image_stride elements apart
     int ldd;
     const float* bias;       // [N] fp32 or nullptr
     const bf16* residual;    // [M, ldr] bf16 or nullptr (added after activation)
@@ -225,8 +226,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             tile_origin(ct, m0, n0);
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < p.M;
-            bf16* dbase = p.D ? p.D : reinterpret_cast<bf16*>(p.io->final_out);
-            bf16* drow = dbase + (size_t)row * p.ldd;
+            bf16* drow;
+            if (p.D) {
+                drow = p.D + (size_t)row * p.ldd;
+            } else {        // caller memory: image b's tokens start at final_out + b * final_image_stride
+                const int bi = row / p.rows_per_image;
+                drow = reinterpret_cast<bf16*>(p.io->final_out) + (size_t)bi * (size_t)p.io->final_image_stride + (size_t)(row - bi * p.rows_per_image) * p.ldd;
+            }
             const bf16* rrow = p.residual ? p.residual + (size_t)row * p.ldr : nullptr;
             // ---- everything that does not depend on the accumulator is fetched BEFORE waiting for it: the bias of this
             // warp's column groups (coalesced, staged in smem for broadcast reads) and the residual row segment of the

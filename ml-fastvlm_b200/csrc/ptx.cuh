@@ -19,6 +19,8 @@ struct IoBlock {
     const void* images;     // NCHW input of the stem
     void* final_out;        // destination of the last unit's output when it is caller memory
     void* tokens_out;       // optional copy-out of the tower tokens when a projector follows
+    long long final_image_stride;   // elements between consecutive images in final_out (N*H when dense; L*H when the
+                                    // destination is a [B, L, H] LLM embedding buffer -- the token splice, llava_arch.py:251-271)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -369,6 +369,7 @@ se_expand_scale_gelu_kernel(const bf16* __restrict__ c, const float* __restrict_
     pdl_launch_dependents();
     pdl_wait();
     bf16* __restrict__ tokens = tokens_or_null ? tokens_or_null : reinterpret_cast<bf16*>(io->final_out);
+    const size_t out_img_stride = tokens_or_null ? (size_t)HW * C : (size_t)io->final_image_stride;
     __shared__ float rs[256];
     __shared__ float ss[128];
     const int b = blockIdx.y, c0 = blockIdx.x * 128;
@@ -390,17 +391,18 @@ se_expand_scale_gelu_kernel(const bf16* __restrict__ c, const float* __restrict_
     for (int p = threadIdx.x >> 6; p < HW; p += 4) {
         const size_t off = ((size_t)b * HW + p) * C + c0 + 2 * cp;
         const float2 v = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(c + off)));
-        *reinterpret_cast<uint32_t*>(tokens + off) = pack_bf16x2(gelu_erf(v.x * s0), gelu_erf(v.y * s1));
+        *reinterpret_cast<uint32_t*>(tokens + (size_t)b * out_img_stride + (size_t)p * C + c0 + 2 * cp) = pack_bf16x2(gelu_erf(v.x * s0), gelu_erf(v.y * s1));
     }
 }
 
 // ====================================================================== IO plumbing
-__global__ void set_io_kernel(IoBlock* io, const void* images, void* final_out, void* tokens_out) {
+__global__ void set_io_kernel(IoBlock* io, const void* images, void* final_out, void* tokens_out, long long final_image_stride) {
     pdl_launch_dependents();
     pdl_wait();                 // the previous forward's last kernels may still be reading the block
     io->images = images;
     io->final_out = final_out;
     io->tokens_out = tokens_out;
+    io->final_image_stride = final_image_stride;
 }
 // tokens (workspace) -> caller buffer, 16 B per thread-iteration
 __global__ void __launch_bounds__(256)

@@ -134,6 +134,23 @@ class Engine:
                                           proj.data_ptr() if proj is not None else None), self.handle)
         return tokens, proj
 
+    def forward_into(self, images, embeds, position):
+        """Write the projected visual tokens of image b straight into embeds[b, position:position+N, :]
+        (embeds: [B, L, H] bf16 CUDA, contiguous).  The splice of llava_arch.py:251-271 as the projector's store."""
+        if self.hidden <= 0:
+            raise L.FvhdError("forward_into needs a plan with a projector")
+        if embeds.dtype != torch.bfloat16 or not embeds.is_contiguous() or embeds.dim() != 3 or embeds.shape[2] != self.hidden:
+            raise L.FvhdError(f"embeds must be contiguous bf16 [B, L, {self.hidden}], got {embeds.dtype} {tuple(embeds.shape)}")
+        B, Lseq = embeds.shape[0], embeds.shape[1]
+        if images.shape[0] != B or position < 0 or position + self.num_tokens > Lseq:
+            raise L.FvhdError(f"cannot place {self.num_tokens} tokens at {position} in a sequence of {Lseq} (batch {images.shape[0]} vs {B})")
+        images = images.contiguous()
+        with torch.cuda.device(self.device):
+            dst = embeds.data_ptr() + position * self.hidden * 2
+            L.check(self.lib.fvhd_forward_strided(self.handle, self._stream(), images.data_ptr(), _img_dtype(images), B, None, dst,
+                                                  Lseq * self.hidden), self.handle)
+        return embeds
+
     def encode_images_host(self, host_images, host_out=None):
         """HOST tensors in, HOST tensor out (bf16): the e2e entry (H2D + forward + D2H inside the call)."""
         B = host_images.shape[0]

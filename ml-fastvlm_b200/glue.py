@@ -22,6 +22,22 @@ def encode_images(model, images):
     return projector(image_features)
 
 
+def splice_visual_tokens(model, input_embeds, images, position):
+    """Row f2: place the projected visual tokens of image b at input_embeds[b, position:position+N] without an
+    intermediate tensor -- the projector GEMM's epilogue stores straight into the LLM embedding buffer
+    (the single-image case of the splice loop in prepare_inputs_labels_for_multimodal, llava_arch.py:251-271)."""
+    tower = model.get_model().get_vision_tower()
+    projector = model.get_model().mm_projector
+    with torch.no_grad():
+        eng = tower.fused_engine(projector)
+        x = images.to(device=tower.device, dtype=tower.dtype)
+        if input_embeds.dtype == torch.bfloat16 and input_embeds.is_contiguous():
+            return eng.forward_into(x, input_embeds, position)
+        _, proj = eng.forward(x, want_tokens=False, want_projected=True)     # other dtypes: one cast-copy, as the reference does
+        input_embeds[:, position:position + proj.shape[1]] = proj.to(input_embeds.dtype)
+        return input_embeds
+
+
 class EncodeImagesMixin:
     """Mix into a `LlavaMetaForCausalLM` subclass to override `encode_images` (llava_arch.py:141-144)."""
 

@@ -283,6 +283,20 @@ def test_tower_and_projector_modules(tower_sd, proj_sd, oracle256, golden_dir, d
     assert rel_l2(fused, split) < 5e-3                  # same kernels; split path rounds tokens through fp32->bf16 once more
 
 
+def test_splice_into_embedding_buffer(eng256, dev):
+    """Row f2: projected tokens written straight into a [B, L, H] LLM embedding buffer at the <image> position."""
+    x = fx.synthetic_images(3, 256, seed=13).to(dev)          # max_batch = 2 -> two passes, strided destination
+    _, proj = eng256.forward(x, False, True)
+    L, pos = 16 + 9, 4
+    emb = torch.full((3, L, 896), 7.0, dtype=torch.bfloat16, device=dev)
+    out = eng256.forward_into(x, emb, pos)
+    assert out.data_ptr() == emb.data_ptr()
+    assert torch.equal(emb[:, pos:pos + 16], proj)                                  # same bits as the dense call
+    assert (emb[:, :pos] == 7).all() and (emb[:, pos + 16:] == 7).all()             # text positions untouched
+    with pytest.raises(pkg.FvhdError):
+        eng256.forward_into(x, emb, L - 3)                                          # does not fit
+
+
 # ------------------------------------------------------------------ bench-size properties (R=1024)
 def test_batch_independence_and_determinism_1024(packed, dev):
     eng = pkg.Engine(1024, 896, 2, 2).load(packed, dev)

@@ -132,3 +132,29 @@ def test_projector_drop_in_surface(proj_sd):
     Cfg.mm_projector_type = "bogus"
     with pytest.raises(ValueError):
         pkg.build_vision_projector(Cfg())
+
+
+def test_checkpoint_ingest_released_layout(tmp_path, tower_sd, proj_sd):
+    """Row f4: a released-style HF folder (sharded safetensors, `model.vision_tower.*` / `model.mm_projector.*` keys among
+    LLM tensors, config.json) loads into the tower + projector modules and packs to the same device weights."""
+    from safetensors.torch import save_file
+    full = {("model.vision_tower." + k): v.contiguous() for k, v in tower_sd.items()}
+    full.update({("model.mm_projector." + k): v.contiguous() for k, v in proj_sd.items()})
+    full["model.embed_tokens.weight"] = torch.zeros(8, 896)            # decoys: LLM tensors must be ignored
+    full["lm_head.weight"] = torch.zeros(8, 896)
+    keys = list(full.keys())
+    half = len(keys) // 2
+    save_file({k: full[k] for k in keys[:half]}, str(tmp_path / "model-00001-of-00002.safetensors"))
+    save_file({k: full[k] for k in keys[half:]}, str(tmp_path / "model-00002-of-00002.safetensors"))
+    json.dump({"mm_vision_tower": "mobileclip_l_256", "hidden_size": 896, "mm_hidden_size": 3072, "mm_projector_type": "mlp2x_gelu"},
+              open(tmp_path / "config.json", "w"))
+    tsd, psd, cfg = pkg.read_state_dicts(str(tmp_path))
+    assert list(tsd.keys()) != [] and set(tsd.keys()) == set(tower_sd.keys()) and set(psd.keys()) == set(proj_sd.keys())
+    tower, proj, cfg = pkg.load_pretrained(str(tmp_path))
+    assert tower.input_image_size == 256 and tower.num_patches == 16
+    a = pkg.pack_tower(tower.state_dict())
+    b = pkg.pack_tower(tower_sd)
+    assert all(torch.equal(a[k], b[k]) for k in b)
+    assert torch.equal(proj.state_dict()["2.weight"], proj_sd["2.weight"])
+    with pytest.raises((KeyError, FileNotFoundError)):
+        pkg.read_state_dicts(str(tmp_path / "nope"))

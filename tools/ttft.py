@@ -39,11 +39,13 @@ def main():
     def one():
         t0 = time.perf_counter()
         img = host_img.to(dev, non_blocking=True)
-        _, vis = eng.forward(img, want_tokens=False, want_projected=True)           # [1,256,896] bf16
+        x = torch.empty(1, n_pre + 256 + n_post, 896, dtype=torch.bfloat16, device=dev)
+        eng.forward_into(img, x, n_pre)             # projector epilogue stores at the <image> position (row f2: no cat)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         txt = embed(ids)
-        x = torch.cat([txt[:, :n_pre], vis, txt[:, n_pre:]], dim=1)                 # splice at the <image> position
+        x[:, :n_pre] = txt[:, :n_pre]
+        x[:, n_pre + 256:] = txt[:, n_pre:]
         out = llm(inputs_embeds=x, use_cache=True)
         tok = out.logits[:, -1].argmax(-1)
         tok.item()                                                                   # first token on the host
