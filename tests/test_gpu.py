@@ -184,6 +184,22 @@ def test_tokens_1024_vs_reference_golden(packed, golden_dir, dev):
     assert rel_l2(tokens.float(), ref) < E2E_TOL
 
 
+def test_encode_images_1536_7b_shape_vs_oracle(tower_sd, dev):
+    """BASELINE configs[4] geometry: R=1536 -> 576 tokens, projector H=3584 (Qwen2-7B).  Maps of 384/192/96/48/24 px: partial
+    16x16 tiles, TMA zero-filled halos past the edge, 2304-key attention."""
+    psd = fx.projector_state_dict(3584)
+    pk = pkg.pack_tower(tower_sd)
+    pk.update(pkg.pack_projector(psd))
+    eng = pkg.Engine(1536, 3584, 2, 1).load(pk, dev)
+    x = fx.synthetic_images(1, 1536, seed=2)
+    tokens, proj = eng.forward(x.to(dev), True, True)
+    assert tuple(tokens.shape) == (1, 576, 3072) and tuple(proj.shape) == (1, 576, 3584)
+    col = {}
+    ref = orc.encode_images(x, tower_sd, psd, col)
+    assert rel_l2(tokens.float(), col["tokens"]) < E2E_TOL
+    assert rel_l2(proj.float(), ref) < E2E_TOL
+
+
 def test_input_dtypes_and_batch_chunking(eng256, dev):
     """fp32 / fp16 / bf16 images; B=5 with max_batch=2 (3 passes) == per-image results, bit-exact.
     The random-weight fixture amplifies an input perturbation ~70x (fp16 rounding of the pixels, 5e-4, moves the
