@@ -9,8 +9,12 @@ namespace fvhd {
 // ====================================================================== stem
 // convolutional_stem blocks 0 and 1 fused (mci.py:567-590): NCHW image (fp32/fp16/bf16) ->
 // conv3x3 s2 (3->96) + GELU -> dw3x3 s2 + GELU -> NHWC bf16 [B, R/4, R/4, 96].
-// The R/2 x R/2 x 96 intermediate (50 MB / image at R=1024) never reaches HBM: a CTA computes the
-// 17x17 conv0 patch its 8x8 output tile needs into shared memory.  Block 2 (1x1 + GELU) is a GEMM.
+// The R/2 x R/2 x 96 intermediate (50 MB / image at R=1024) never reaches HBM: a CTA computes the 17x17 conv0 patch its
+// 8x8 output tile needs into shared memory.  conv0 is an implicit GEMM on the tensor cores (mma.sync m16n8k16, f16 inputs --
+// 11-bit significands hold both the k/255 pixel grid and the weights more precisely than bf16 -- fp32 accumulate):
+// M = 289 patch pixels (19 m-tiles), N = 96, K = 27 taps padded to 32; A fragments are gathered directly from the staged
+// fp16 input patch (no im2col buffer), the 48 B-fragment registers hold all of w0 for the CTA's lifetime.
+// Block 2 (1x1 + GELU) is a tcgen05 GEMM launch.
 constexpr int STEM_C = 96;
 constexpr int STEM_TO = 8;                       // output tile (at R/4)
 constexpr int STEM_MID = 2 * STEM_TO + 1;        // 17: conv0 patch edge
@@ -18,24 +22,33 @@ constexpr int STEM_IN = 2 * STEM_MID + 1;        // 35: input patch edge
 constexpr int STEM_INP = STEM_IN + 1;            // 36: padded pitch
 constexpr int STEM_MIDP = STEM_C / 2 + 1;        // 49 words per conv0 pixel (bf16 pairs, +1 pad)
 constexpr int STEM_THREADS = 256;
-constexpr size_t STEM_SMEM = (size_t)(3 * STEM_IN * STEM_INP + STEM_MID * STEM_MID * STEM_MIDP + 27 * STEM_C + 9 * STEM_C + 2 * STEM_C) * 4;
+constexpr int STEM_NPIX = STEM_MID * STEM_MID;   // 289
+constexpr int STEM_MT = (STEM_NPIX + 15) / 16;   // 19 m-tiles
+constexpr size_t STEM_SMEM = (size_t)32 * STEM_C * 2 /*w0 fp16 [32][96]*/ + (size_t)(9 * STEM_C + 2 * STEM_C) * 4 /*w1, b0, b1*/ +
+                             (size_t)3 * STEM_IN * STEM_INP * 2 /*input patch fp16*/ + 16 + (size_t)STEM_NPIX * STEM_MIDP * 4 /*conv0 out*/;
 
 template <typename T> __device__ __forceinline__ float img_ld(const T* p);
 template <> __device__ __forceinline__ float img_ld<float>(const float* p) { return __ldg(p); }
 template <> __device__ __forceinline__ float img_ld<__half>(const __half* p) { return __half2float(*p); }
 template <> __device__ __forceinline__ float img_ld<bf16>(const bf16* p) { return __bfloat162float(*p); }
 
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(STEM_THREADS)
 stem_kernel(const IoBlock* __restrict__ io, bf16* __restrict__ out, const float* __restrict__ w0 /*[27][96], k=(ci*3+ky)*3+kx*/,
             const float* __restrict__ b0, const float* __restrict__ w1 /*[9][96]*/, const float* __restrict__ b1, int R, int tiles_x) {
-    extern __shared__ __align__(16) float stem_smem[];
-    float* w0s = stem_smem;                                              // [27][96], float4 reads: 16-B aligned at the base
-    float* w1s = w0s + 27 * STEM_C;                                      // [9][96]
+    extern __shared__ __align__(16) uint8_t stem_smem_raw[];
+    __half* w0h = reinterpret_cast<__half*>(stem_smem_raw);                       // [32][96], rows 27..31 zero
+    float* w1s = reinterpret_cast<float*>(w0h + 32 * STEM_C);                     // [9][96]
     float* b0s = w1s + 9 * STEM_C;
     float* b1s = b0s + STEM_C;
-    float* sin = b1s + STEM_C;                                           // [3][35][36]
-    uint32_t* s1 = reinterpret_cast<uint32_t*>(sin + 3 * STEM_IN * STEM_INP);   // [289][49]
+    __half* sin = reinterpret_cast<__half*>(b1s + STEM_C);                        // [3][35][36]
+    uint32_t* s1 = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(sin) + ((3 * STEM_IN * STEM_INP * 2 + 15) / 16) * 16);   // [289][49]
 
     pdl_launch_dependents();
     const int b = blockIdx.z;
@@ -44,7 +57,7 @@ stem_kernel(const IoBlock* __restrict__ io, bf16* __restrict__ out, const float*
     const int iy0 = 4 * ty0 - 3, ix0 = 4 * tx0 - 3;     // input patch origin
     const int cy0 = 2 * ty0 - 1, cx0 = 2 * tx0 - 1;     // conv0 patch origin
 
-    for (int i = threadIdx.x; i < 27 * STEM_C; i += STEM_THREADS) w0s[i] = __ldg(w0 + i);
+    for (int i = threadIdx.x; i < 32 * STEM_C; i += STEM_THREADS) w0h[i] = __float2half_rn(i < 27 * STEM_C ? __ldg(w0 + i) : 0.f);
     for (int i = threadIdx.x; i < 9 * STEM_C; i += STEM_THREADS) w1s[i] = __ldg(w1 + i);
     if (threadIdx.x < STEM_C) { b0s[threadIdx.x] = __ldg(b0 + threadIdx.x); b1s[threadIdx.x] = __ldg(b1 + threadIdx.x); }
     pdl_wait();                                                          // io block is written by set_io_kernel
@@ -56,44 +69,82 @@ stem_kernel(const IoBlock* __restrict__ io, bf16* __restrict__ out, const float*
         const int gy = iy0 + yy, gx = ix0 + xx;
         float v = 0.f;
         if (gy >= 0 && gy < R && gx >= 0 && gx < R) v = img_ld<T>(img + (((size_t)b * 3 + ci) * R + gy) * R + gx);
-        sin[(ci * STEM_IN + yy) * STEM_INP + xx] = v;
+        sin[(ci * STEM_IN + yy) * STEM_INP + xx] = __float2half_rn(v);
     }
     __syncthreads();
 
-    // phase 1: conv0 3x3 s2 + GELU on the 17x17 patch; item = (24-channel group, pixel)
-    for (int it = threadIdx.x; it < 4 * STEM_MID * STEM_MID; it += STEM_THREADS) {
-        const int g = it / (STEM_MID * STEM_MID);
-        const int p = it - g * STEM_MID * STEM_MID;
-        const int py = p / STEM_MID, px = p - py * STEM_MID;
-        const int cy = cy0 + py, cx = cx0 + px;
-        uint32_t* dst = s1 + p * STEM_MIDP + g * 12;
-        if (cy < 0 || cy >= R2 || cx < 0 || cx >= R2) {     // zero padding of the depthwise conv
+    // phase 1: conv0 3x3 s2 + GELU on the 17x17 patch as an implicit GEMM on the tensor cores
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int g = lane >> 2, t = lane & 3;
+        const uint16_t* w0u = reinterpret_cast<const uint16_t*>(w0h);
+        const uint16_t* sinu = reinterpret_cast<const uint16_t*>(sin);
+        // B fragments of all 12 n-tiles x 2 k-steps: {w0[k][n], w0[k+1][n]}, {w0[k+8][n], w0[k+9][n]}, n = 8 nt + g
+        uint32_t bf[12][2][2];
 #pragma unroll
-            for (int j = 0; j < 12; ++j) dst[j] = 0u;
-            continue;
-        }
-        float acc[24];
+        for (int nt = 0; nt < 12; ++nt)
 #pragma unroll
-        for (int j = 0; j < 24; ++j) acc[j] = b0s[g * 24 + j];
+            for (int s = 0; s < 2; ++s)
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const float xv = sin[(ci * STEM_IN + 2 * py + ky) * STEM_INP + 2 * px + kx];
-                    const float4* wp = reinterpret_cast<const float4*>(w0s + ((ci * 3 + ky) * 3 + kx) * STEM_C + g * 24);
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        const float4 w = wp[j];
-                        acc[4 * j + 0] = fmaf(xv, w.x, acc[4 * j + 0]);
-                        acc[4 * j + 1] = fmaf(xv, w.y, acc[4 * j + 1]);
-                        acc[4 * j + 2] = fmaf(xv, w.z, acc[4 * j + 2]);
-                        acc[4 * j + 3] = fmaf(xv, w.w, acc[4 * j + 3]);
-                    }
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int k = 16 * s + 2 * t + 8 * h2, n = nt * 8 + g;
+                    bf[nt][s][h2] = (uint32_t)w0u[k * STEM_C + n] | ((uint32_t)w0u[(k + 1) * STEM_C + n] << 16);
                 }
+        // patch offsets of this thread's 8 K indices: k -> (ci, ky, kx) -> (ci*35 + ky)*36 + kx  (k >= 27: weight is zero)
+        int koff[2][2][2];
 #pragma unroll
-        for (int j = 0; j < 12; ++j) dst[j] = pack_bf16x2(gelu_erf(acc[2 * j]), gelu_erf(acc[2 * j + 1]));
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = 16 * s + 2 * t + 8 * h2 + e;
+                    const int kk = k < 27 ? k : 0;
+                    const int ci = kk / 9, r9 = kk - ci * 9, ky = r9 / 3, kx = r9 - ky * 3;
+                    koff[s][h2][e] = (ci * STEM_IN + ky) * STEM_INP + kx;
+                }
+        for (int mt = warp; mt < STEM_MT; mt += STEM_THREADS / 32) {
+            int pix[2], base[2];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                int pp = mt * 16 + g + 8 * rr;
+                pix[rr] = pp;
+                if (pp > STEM_NPIX - 1) pp = STEM_NPIX - 1;          // padded rows: computed, never stored
+                const int py = pp / STEM_MID, px = pp - py * STEM_MID;
+                base[rr] = (2 * py) * STEM_INP + 2 * px;
+            }
+            uint32_t af[2][4];
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr)
+                        af[s][h2 * 2 + rr] = (uint32_t)sinu[base[rr] + koff[s][h2][0]] | ((uint32_t)sinu[base[rr] + koff[s][h2][1]] << 16);
+            float d[12][4];
+#pragma unroll
+            for (int nt = 0; nt < 12; ++nt) {
+                d[nt][0] = d[nt][1] = d[nt][2] = d[nt][3] = 0.f;
+                mma_f16_16816(d[nt], af[0], bf[nt][0][0], bf[nt][0][1]);
+                mma_f16_16816(d[nt], af[1], bf[nt][1][0], bf[nt][1][1]);
+            }
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int pp = pix[rr];
+                if (pp >= STEM_NPIX) continue;
+                const int py = pp / STEM_MID, px = pp - py * STEM_MID;
+                const int cy = cy0 + py, cx = cx0 + px;
+                const bool inside = cy >= 0 && cy < R2 && cx >= 0 && cx < R2;      // outside: zero padding of the depthwise conv
+                uint32_t* dst = s1 + pp * STEM_MIDP + t;
+#pragma unroll
+                for (int nt = 0; nt < 12; ++nt) {
+                    const int ch = nt * 8 + 2 * t;
+                    const float v0 = gelu_erf(d[nt][2 * rr + 0] + b0s[ch]);
+                    const float v1 = gelu_erf(d[nt][2 * rr + 1] + b0s[ch + 1]);
+                    dst[nt * 4] = inside ? pack_bf16x2(v0, v1) : 0u;
+                }
+            }
+        }
     }
     __syncthreads();
 
