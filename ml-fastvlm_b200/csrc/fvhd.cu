@@ -611,7 +611,7 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
                 return launch_k(se_reduce_kernel, dim3(kSeRd / 8, batch), dim3(256), 0, s, pooled, wr, br, sr, 3072, kSeRd);
             }, "se_reduce_kernel", U, 2.0 * batch * 3072 * kSeRd, 2.0 * 3072 * kSeRd);
             pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
-                return launch_k(se_expand_scale_gelu_kernel, dim3(3072 / 128, batch), dim3(256), 0, s, cexp, sr, we, be, dst, io, HW, 3072, kSeRd);
+                return launch_k(se_expand_scale_gelu_kernel, dim3(3072 / 64, batch), dim3(256), 0, s, cexp, sr, we, be, dst, io, HW, 3072, kSeRd);
             }, "se_expand_scale_gelu_kernel", U, 2.0 * batch * 3072 * kSeRd, 4.0 * Md * 3072 + 2.0 * 3072 * kSeRd);
             break;
         }

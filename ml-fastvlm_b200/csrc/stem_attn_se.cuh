@@ -413,7 +413,8 @@ se_reduce_kernel(const float* __restrict__ pooled, const bf16* __restrict__ wr /
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if (lane == 0) r[(size_t)b * RD + j] = fmaxf(a + __ldg(br + j), 0.f);
 }
-// grid (C/128, B): expand + sigmoid for a 128-channel slice, then scale + GELU all HW pixels of it.
+// grid (C/64, B): expand + sigmoid for a 64-channel slice (one warp per channel: 192-term dot product across the lanes),
+// then scale + GELU all HW pixels of that slice.
 __global__ void __launch_bounds__(256)
 se_expand_scale_gelu_kernel(const bf16* __restrict__ c, const float* __restrict__ r, const bf16* __restrict__ we /*[C][RD]*/,
                             const float* __restrict__ be, bf16* __restrict__ tokens_or_null, const IoBlock* __restrict__ io, int HW, int C, int RD) {
@@ -422,24 +423,27 @@ se_expand_scale_gelu_kernel(const bf16* __restrict__ c, const float* __restrict_
     bf16* __restrict__ tokens = tokens_or_null ? tokens_or_null : reinterpret_cast<bf16*>(io->final_out);
     const size_t out_img_stride = tokens_or_null ? (size_t)HW * C : (size_t)io->final_image_stride;
     __shared__ float rs[256];
-    __shared__ float ss[128];
-    const int b = blockIdx.y, c0 = blockIdx.x * 128;
+    __shared__ float ss[64];
+    const int b = blockIdx.y, c0 = blockIdx.x * 64;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < RD; i += 256) rs[i] = r[(size_t)b * RD + i];
     __syncthreads();
-    if (threadIdx.x < 128) {
-        const int ch = c0 + threadIdx.x;
-        float a = __ldg(be + ch);
-        for (int j = 0; j < RD; j += 8) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(we + (size_t)ch * RD + j));
-            const float2 w0 = unpack_bf16x2(u.x), w1 = unpack_bf16x2(u.y), w2 = unpack_bf16x2(u.z), w3 = unpack_bf16x2(u.w);
-            a += w0.x * rs[j] + w0.y * rs[j + 1] + w1.x * rs[j + 2] + w1.y * rs[j + 3] + w2.x * rs[j + 4] + w2.y * rs[j + 5] + w3.x * rs[j + 6] + w3.y * rs[j + 7];
+    for (int k = 0; k < 8; ++k) {                       // 8 warps x 8 channels
+        const int ch = c0 + warp * 8 + k;
+        float a = 0.f;
+        for (int j = lane * 2; j < RD; j += 64) {
+            const float2 w = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(we + (size_t)ch * RD + j)));
+            a = fmaf(w.x, rs[j], a);
+            a = fmaf(w.y, rs[j + 1], a);
         }
-        ss[threadIdx.x] = 1.0f / (1.0f + __expf(-a));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) ss[warp * 8 + k] = 1.0f / (1.0f + __expf(-(a + __ldg(be + ch))));
     }
     __syncthreads();
-    const int cp = threadIdx.x & 63;
+    const int cp = threadIdx.x & 31;
     const float s0 = ss[2 * cp], s1 = ss[2 * cp + 1];
-    for (int p = threadIdx.x >> 6; p < HW; p += 4) {
+    for (int p = threadIdx.x >> 5; p < HW; p += 8) {
         const size_t off = ((size_t)b * HW + p) * C + c0 + 2 * cp;
         const float2 v = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(c + off)));
         *reinterpret_cast<uint32_t*>(tokens + (size_t)b * out_img_stride + (size_t)p * C + c0 + 2 * cp) = pack_bf16x2(gelu_erf(v.x * s0), gelu_erf(v.y * s1));
