@@ -128,6 +128,18 @@ int fvhd_profile_steps(fvhd_handle h, void* stream, const void* images, int img_
 /* Number of kernel launches one forward of `batch` images enqueues. */
 int fvhd_launches_per_forward(fvhd_handle h, int batch);
 
+/* ---- row f1: the reference's CPU preprocessing on the GPU, bit-exact ----
+ * replaces: process_images (llava/mm_utils.py:168-184) -> CLIPImageProcessor.preprocess as configured by
+ * mobileclip_encoder.py:45-49 (pinned transformers 4.48.3 = PIL path): resize shortest edge to R with PIL BICUBIC, centre crop
+ * R x R, x 1/255, mean 0 / std 1, CHW; pad_to_square = the 'pad' aspect mode (expand2square, mm_utils.py:154-165).
+ *   rgb   uint8 RGB, HWC [H, W, 3]; device memory, or host memory when src_on_host != 0 (copied with cudaMemcpyAsync)
+ *   out   device, [3, R, R] of out_dtype (one image of the tower's input batch) */
+int fvhd_preprocess(fvhd_handle h, void* stream, const void* rgb, int src_on_host, int H, int W, int pad_to_square,
+                    void* out, int out_dtype);
+/* Host-only: Pillow's fixed-point bicubic coefficient table for resampling in_size -> out_size (Resample.c precompute_coeffs +
+ * normalize_coeffs_8bpc).  bounds [out][2] = (first source index, tap count); kk [out][ksize]; returns ksize (or < 0). */
+int fvhd_resample_coeffs(int in_size, int out_size, int* bounds, int* kk, int kk_capacity);
+
 /* Debug: subsequent fvhd_gemm calls write 16 globaltimer stamps per CTA into `dev_buf` (NULL = off), optionally with a
  * forced N tile (0 = cost model) and a cluster-size cap (1/2/4).  Process-global; not for production use. */
 int fvhd_debug_gemm_trace(void* dev_buf_16_u64_per_cta, int force_bn, int max_cs);

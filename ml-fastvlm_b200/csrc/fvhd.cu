@@ -18,6 +18,7 @@
 #include "dwconv.cuh"
 #include "gemm_tcgen05.cuh"
 #include "mlp_fused.cuh"
+#include "preprocess.cuh"
 #include "stem_attn_se.cuh"
 
 using namespace fvhd;
@@ -85,6 +86,12 @@ struct fvhd_handle_s {
     std::map<int, Plan> plans;
     int64_t act0 = 0;           // elements of the largest activation per image: (R/4)^2 * 96
     void *stage_in = nullptr, *stage_out = nullptr;   // fvhd_encode_images_host device staging
+    // row f1 (preprocess): device coefficient tables cached per (in_size, out_size), horizontal-pass scratch, 1/255 LUT
+    struct RsTable { int* bounds; int* kk; int ksize; };
+    std::map<std::pair<int, int>, RsTable> rs_tables;
+    uint8_t* rs_tmp = nullptr; size_t rs_tmp_bytes = 0;
+    uint8_t* rs_src = nullptr; size_t rs_src_bytes = 0;
+    float* rs_lut = nullptr;
     size_t stage_in_bytes = 0, stage_out_bytes = 0;
 };
 
@@ -753,6 +760,10 @@ int fvhd_destroy(fvhd_handle h) {
         if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
         if (h->stage_in) cudaFree(h->stage_in);
         if (h->stage_out) cudaFree(h->stage_out);
+        for (auto& kv : h->rs_tables) { cudaFree(kv.second.bounds); cudaFree(kv.second.kk); }
+        if (h->rs_tmp) cudaFree(h->rs_tmp);
+        if (h->rs_src) cudaFree(h->rs_src);
+        if (h->rs_lut) cudaFree(h->rs_lut);
     }
     delete h;
     return FVHD_OK;
@@ -1014,6 +1025,97 @@ int fvhd_profile_steps(fvhd_handle h, void* stream, const void* images, int img_
     CUDA_TRY(h, cudaStreamSynchronize(st));
     for (int i = 0; i < n; ++i) CUDA_TRY(h, cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
     for (auto& e : ev) cudaEventDestroy(e);
+    return FVHD_OK;
+}
+
+// ---------------------------------------------------------------- row f1: preprocessing
+int fvhd_resample_coeffs(int in_size, int out_size, int* bounds, int* kk, int kk_capacity) {
+    if (in_size < 1 || out_size < 1) return FVHD_ERR_INVALID;
+    std::vector<int> b, k;
+    const int ksize = resample_coeffs(in_size, out_size, b, k);
+    if (bounds) memcpy(bounds, b.data(), b.size() * sizeof(int));
+    if (kk) {
+        if ((size_t)kk_capacity < k.size()) return FVHD_ERR_INVALID;
+        memcpy(kk, k.data(), k.size() * sizeof(int));
+    }
+    return ksize;
+}
+
+static int rs_get_table(fvhd_handle h, int in_size, int out_size, fvhd_handle_s::RsTable* out) {
+    auto key = std::make_pair(in_size, out_size);
+    auto it = h->rs_tables.find(key);
+    if (it == h->rs_tables.end()) {
+        std::vector<int> b, k;
+        fvhd_handle_s::RsTable t{};
+        t.ksize = resample_coeffs(in_size, out_size, b, k);
+        CUDA_TRY(h, cudaMalloc(&t.bounds, b.size() * sizeof(int)));
+        CUDA_TRY(h, cudaMalloc(&t.kk, k.size() * sizeof(int)));
+        CUDA_TRY(h, cudaMemcpy(t.bounds, b.data(), b.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_TRY(h, cudaMemcpy(t.kk, k.data(), k.size() * sizeof(int), cudaMemcpyHostToDevice));
+        it = h->rs_tables.emplace(key, t).first;
+    }
+    *out = it->second;
+    return FVHD_OK;
+}
+
+int fvhd_preprocess(fvhd_handle h, void* stream, const void* rgb, int src_on_host, int H, int W, int pad_to_square, void* out, int out_dtype) {
+    if (!h) return FVHD_ERR_INVALID;
+    int rc = ensure_cuda(h);
+    if (rc != FVHD_OK) return rc;
+    if (!rgb || !out || H < 1 || W < 1) return fail(h, FVHD_ERR_INVALID, "fvhd_preprocess: bad image %dx%d", H, W);
+    if (out_dtype < FVHD_F32 || out_dtype > FVHD_BF16) return fail(h, FVHD_ERR_INVALID, "fvhd_preprocess: bad output dtype %d", out_dtype);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int R = h->R;
+    // expand2square (mm_utils.py:154-165): canvas Hs x Ws with the image at (offy, offx)
+    const int Hs = pad_to_square ? (H > W ? H : W) : H, Ws = pad_to_square ? Hs : W;
+    const int offy = pad_to_square && W > H ? (W - H) / 2 : 0, offx = pad_to_square && H > W ? (H - W) / 2 : 0;
+    // get_resize_output_image_size(size = R, default_to_square = False)
+    const int shortE = Ws <= Hs ? Ws : Hs, longE = Ws <= Hs ? Hs : Ws;
+    const int new_long = (int)((double)R * longE / shortE);
+    const int oh = Ws <= Hs ? new_long : R, ow = Ws <= Hs ? R : new_long;
+    const int top = (oh - R) / 2, left = (ow - R) / 2;
+    if (!h->rs_lut) {
+        float lut[256];
+        for (int i = 0; i < 256; ++i) lut[i] = (float)((double)i * (1.0 / 255.0));      // transformers rescale(): float64 multiply
+        CUDA_TRY(h, cudaMalloc(&h->rs_lut, sizeof(lut)));
+        CUDA_TRY(h, cudaMemcpy(h->rs_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+    }
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(rgb);
+    if (src_on_host) {
+        const size_t nb = (size_t)H * W * 3;
+        if (h->rs_src_bytes < nb) {
+            if (h->rs_src) cudaFree(h->rs_src);
+            h->rs_src = nullptr; h->rs_src_bytes = 0;
+            CUDA_TRY(h, cudaMalloc(&h->rs_src, nb));
+            h->rs_src_bytes = nb;
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(h->rs_src, rgb, nb, cudaMemcpyHostToDevice, st));
+        src = h->rs_src;
+    }
+    const size_t tmp_bytes = (size_t)Hs * ow * 3;
+    if (h->rs_tmp_bytes < tmp_bytes) {
+        if (h->rs_tmp) cudaFree(h->rs_tmp);
+        h->rs_tmp = nullptr; h->rs_tmp_bytes = 0;
+        CUDA_TRY(h, cudaMalloc(&h->rs_tmp, tmp_bytes));
+        h->rs_tmp_bytes = tmp_bytes;
+    }
+    fvhd_handle_s::RsTable tx{}, ty{};
+    const dim3 g1((ow + 127) / 128, Hs);
+    cudaError_t e;
+    if (ow != Ws) {
+        if ((rc = rs_get_table(h, Ws, ow, &tx)) != FVHD_OK) return rc;
+        e = launch_k(resample_h_kernel, g1, dim3(128), 0, st, src, H, W, offy, offx, Ws, h->rs_tmp, ow, (const int*)tx.bounds, (const int*)tx.kk, tx.ksize);
+    } else {
+        e = launch_k(pad_copy_kernel, g1, dim3(128), 0, st, src, H, W, offy, offx, h->rs_tmp, ow);
+    }
+    if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "preprocess horizontal pass: %s", cudaGetErrorString(e));
+    // vertical pass (identity table when oh == Hs: one tap of weight 1 << 22 -> exact copy)
+    if ((rc = rs_get_table(h, Hs, oh, &ty)) != FVHD_OK) return rc;
+    const dim3 g2((R + 127) / 128, R);
+    if (out_dtype == FVHD_F32) e = launch_k(resample_v_crop_kernel<float>, g2, dim3(128), 0, st, (const uint8_t*)h->rs_tmp, ow, (float*)out, R, top, left, (const int*)ty.bounds, (const int*)ty.kk, ty.ksize, (const float*)h->rs_lut);
+    else if (out_dtype == FVHD_F16) e = launch_k(resample_v_crop_kernel<__half>, g2, dim3(128), 0, st, (const uint8_t*)h->rs_tmp, ow, (__half*)out, R, top, left, (const int*)ty.bounds, (const int*)ty.kk, ty.ksize, (const float*)h->rs_lut);
+    else e = launch_k(resample_v_crop_kernel<bf16>, g2, dim3(128), 0, st, (const uint8_t*)h->rs_tmp, ow, (bf16*)out, R, top, left, (const int*)ty.bounds, (const int*)ty.kk, ty.ksize, (const float*)h->rs_lut);
+    if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "preprocess vertical pass: %s", cudaGetErrorString(e));
     return FVHD_OK;
 }
 

@@ -46,6 +46,8 @@ SYMBOLS = {
     "fvhd_step_info": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "fvhd_profile_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int]),
     "fvhd_launches_per_forward": (C.c_int, [C.c_void_p, C.c_int]),
+    "fvhd_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "fvhd_resample_coeffs": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]),
     "fvhd_debug_gemm_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "fvhd_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                             C.c_int, C.c_int, C.c_int, C.c_int]),
