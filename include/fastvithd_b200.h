@@ -148,6 +148,13 @@ int fvhd_debug_gemm_trace(void* dev_buf_16_u64_per_cta, int force_bn, int max_cs
 int fvhd_gemm(fvhd_handle h, void* stream, const void* A, const void* W, const void* bias, const void* residual,
               void* D, int M, int N, int K, int act);
 
+/* Stand-alone fused ConvFFN entry (tests, traces): out[M,C] = resid + fc2(GELU(fc1(z) + b1)) + b2  (mci.py:922-926 with the
+ * layer scale folded into w2 / b2), bf16 operands, fp32 biases; w1 [4C, C], w2 [C, 4C] row-major.  C = 96 / 192 run the
+ * single-CTA kernel, C = 384 the 4-CTA-cluster kernel (hidden split across the cluster, DSMEM reduction); `trace` (C = 384
+ * only, may be NULL) receives 64 globaltimer stamps per CTA. */
+int fvhd_convffn(fvhd_handle h, void* stream, const void* z, const void* w1, const void* b1, const void* w2, const void* b2,
+                 const void* resid, void* out, int M, int C, void* trace_64_u64_per_cta);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@
 #include "dwconv.cuh"
 #include "gemm_tcgen05.cuh"
 #include "mlp_fused.cuh"
+#include "mlp_cluster.cuh"
 #include "preprocess.cuh"
 #include "stem_attn_se.cuh"
 
@@ -81,6 +82,7 @@ struct fvhd_handle_s {
     size_t ws_bytes = 0;
     EncodeTiledFn encode = nullptr;
     int num_sms = 148;
+    int mlpc_clusters = 0;        // resident 4-CTA clusters of mlp_cluster_tcgen05_kernel (cudaOccupancyMaxActiveClusters)
     bool use_graph = true;
     cudaStream_t cap_stream = nullptr;   // private stream used only to capture graphs (the legacy default stream cannot be captured)
     std::map<int, Plan> plans;
@@ -264,6 +266,7 @@ Buffers carve(fvhd_handle h, int batch) {
 bool g_use_pdl = true;
 int g_gemm_max_cs = 1;        // FVHD_GEMM_CS=1|2|4 caps the GEMM cluster size.  Default 1: at batch 1 the delivered-bytes rate is
                               // the limit and multicast only reduces L2 reads -- measured no gain (profiles/r01_f_summary.md)
+bool g_use_cluster_mlp = true; // FVHD_NO_CLUSTER_MLP=1: stage-2 (C = 384) ConvFFN as two GEMM launches instead of the 4-CTA-cluster kernel
 bool g_use_fused_mlp = true;  // FVHD_NO_FUSED_MLP=1: ConvFFN as two GEMM launches (reference path of the bit-exactness test)
 unsigned long long* g_gemm_trace = nullptr;   // fvhd_debug_gemm_trace: device buffer, 16 stamps per CTA
 int g_force_bn = 0;                            // fvhd_debug_gemm_trace: force the N tile (0 = cost model)
@@ -318,9 +321,24 @@ int ensure_cuda(fvhd_handle h) {
     { const char* e = getenv("FVHD_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
     { const char* e = getenv("FVHD_NO_PDL"); g_use_pdl = !(e && e[0] == '1'); }
     { const char* e = getenv("FVHD_NO_FUSED_MLP"); g_use_fused_mlp = !(e && e[0] == '1'); }
+    { const char* e = getenv("FVHD_NO_CLUSTER_MLP"); g_use_cluster_mlp = g_use_fused_mlp && !(e && e[0] == '1'); }
     { const char* e = getenv("FVHD_GEMM_CS"); if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) g_gemm_max_cs = e[0] - '0'; }
     CUDA_TRY(h, set_smem(gemm_bf16_tcgen05_kernel, 227 * 1024));
     CUDA_TRY(h, set_smem(mlp_fused_tcgen05_kernel, 227 * 1024));
+    CUDA_TRY(h, set_smem(mlp_cluster_tcgen05_kernel, MLPC_SMEM));
+    {   // how many 4-CTA clusters of the stage-2 ConvFFN kernel can be resident at once (GPC granularity)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(prop.multiProcessorCount / MLPC_CS * MLPC_CS));
+        cfg.blockDim = dim3(MLPC_THREADS);
+        cfg.dynamicSmemBytes = MLPC_SMEM;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = MLPC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, mlp_cluster_tcgen05_kernel, &cfg) != cudaSuccess) { nc = 0; (void)cudaGetLastError(); }
+        h->mlpc_clusters = nc;
+    }
     CUDA_TRY(h, set_smem(repmixer_dw_kernel<16, 16, 256>, MixCfgT<16, 16>::SMEM));
     CUDA_TRY(h, set_smem(repmixer_dw_kernel<8, 16, 128>, MixCfgT<8, 16>::SMEM));
     CUDA_TRY(h, set_smem(dwconv_kernel<7, 1, 1, 0, 16, 16, 8>, DwCfg<7, 1, 1, 16, 16>::SMEM));
@@ -495,21 +513,59 @@ int add_convffn_steps(fvhd_handle h, Plan& pl, int unit, const std::string& p, c
 }
 
 // ConvFFN of a RepMixer block as ONE kernel (C in {96, 192}): hidden stays in TMEM / smem (mlp_fused.cuh).
-int add_fused_mlp_step(fvhd_handle h, Plan& pl, int unit, const std::string& p, const bf16* z, const bf16* resid, bf16* out, int M, int c) {
+int make_fused_mlp_step(fvhd_handle h, Step* st, const bf16* z, const bf16* w1, const float* b1, const bf16* w2, const float* b2,
+                        const bf16* resid, bf16* out, int M, int c) {
     MlpParams mp{};
     mp.M = M; mp.C = c; mp.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
-    mp.b1 = WF(h, p + "fc1.b"); mp.b2 = WF(h, p + "fc2.b"); mp.resid = resid; mp.D = out;
+    mp.b1 = b1; mp.b2 = b2; mp.resid = resid; mp.D = out;
     CUtensorMap tz, tw1, tw2, td;
     int rc;
     if ((rc = make_tmap(h, &tz, z, M, c, c, GEMM_BM)) != FVHD_OK) return rc;
-    if ((rc = make_tmap(h, &tw1, WB(h, p + "fc1.w"), 4 * c, c, c, MLP_NH)) != FVHD_OK) return rc;
-    if ((rc = make_tmap(h, &tw2, WB(h, p + "fc2.w"), c, 4 * c, 4 * c, c)) != FVHD_OK) return rc;
+    if ((rc = make_tmap(h, &tw1, w1, 4 * c, c, c, MLP_NH)) != FVHD_OK) return rc;
+    if ((rc = make_tmap(h, &tw2, w2, c, 4 * c, 4 * c, c)) != FVHD_OK) return rc;
     if ((rc = make_tmap(h, &td, out, M, c, c, 32, 64)) != FVHD_OK) return rc;
     const dim3 grid((unsigned)(mp.tiles_m < h->num_sms ? mp.tiles_m : h->num_sms));
     const size_t smem = mlp_smem_bytes(c);
-    pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+    *st = [=](cudaStream_t s, const RunCtx&) -> cudaError_t {
         return launch_k(mlp_fused_tcgen05_kernel, grid, dim3(MLP_THREADS), smem, s, tz, tw1, tw2, td, mp);
-    }, "mlp_fused_tcgen05_kernel", unit, 2.0 * gemm_flops(M, 4 * c, c), 2.0 * (3.0 * M * c + 8.0 * c * c) + 20.0 * c);
+    };
+    return FVHD_OK;
+}
+int add_fused_mlp_step(fvhd_handle h, Plan& pl, int unit, const std::string& p, const bf16* z, const bf16* resid, bf16* out, int M, int c) {
+    Step st;
+    int rc = make_fused_mlp_step(h, &st, z, WB(h, p + "fc1.w"), WF(h, p + "fc1.b"), WB(h, p + "fc2.w"), WF(h, p + "fc2.b"), resid, out, M, c);
+    if (rc != FVHD_OK) return rc;
+    pl.add(st, "mlp_fused_tcgen05_kernel", unit, 2.0 * gemm_flops(M, 4 * c, c), 2.0 * (3.0 * M * c + 8.0 * c * c) + 20.0 * c);
+    return FVHD_OK;
+}
+
+// Stage-2 ConvFFN (C = 384): one 4-CTA cluster per 128-pixel tile, hidden split across the cluster, DSMEM reduction.
+int make_cluster_mlp_step(fvhd_handle h, Step* st, const bf16* z, const bf16* w1, const float* b1, const bf16* w2, const float* b2,
+                          const bf16* resid, bf16* out, int M, unsigned long long* trace) {
+    const int c = MLPC_C;
+    if (h->mlpc_clusters <= 0) return fail(h, FVHD_ERR_CUDA, "no resident 4-CTA cluster for the stage-2 ConvFFN kernel");
+    MlpParams mp{};
+    mp.M = M; mp.C = c; mp.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+    mp.b1 = b1; mp.b2 = b2; mp.resid = resid; mp.D = out; mp.trace = trace;
+    { const char* e = getenv("FVHD_MLP_STAGGER"); mp.stagger = (e && e[0] == '1') ? 1 : 0; }
+    CUtensorMap tz, tw1, tw2;
+    int rc;
+    if ((rc = make_tmap(h, &tz, z, M, c, c, GEMM_BM)) != FVHD_OK) return rc;
+    if ((rc = make_tmap(h, &tw1, w1, 4 * c, c, c, MLP_NH)) != FVHD_OK) return rc;
+    if ((rc = make_tmap(h, &tw2, w2, c, 4 * c, 4 * c, MLPC_NHALF)) != FVHD_OK) return rc;
+    const int clusters = mp.tiles_m < h->mlpc_clusters ? mp.tiles_m : h->mlpc_clusters;
+    const dim3 grid((unsigned)(clusters * MLPC_CS));
+    *st = [=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+        return launch_kc(MLPC_CS, mlp_cluster_tcgen05_kernel, grid, dim3(MLPC_THREADS), MLPC_SMEM, s, tz, tw1, tw2, mp);
+    };
+    return FVHD_OK;
+}
+int add_cluster_mlp_step(fvhd_handle h, Plan& pl, int unit, const std::string& p, const bf16* z, const bf16* resid, bf16* out, int M) {
+    const int c = MLPC_C;
+    Step st;
+    int rc = make_cluster_mlp_step(h, &st, z, WB(h, p + "fc1.w"), WF(h, p + "fc1.b"), WB(h, p + "fc2.w"), WF(h, p + "fc2.b"), resid, out, M, nullptr);
+    if (rc != FVHD_OK) return rc;
+    pl.add(st, "mlp_cluster_tcgen05_kernel", unit, 2.0 * gemm_flops(M, 4 * c, c), 2.0 * (3.0 * M * c + 8.0 * c * c) + 20.0 * c);
     return FVHD_OK;
 }
 
@@ -569,6 +625,8 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
             }, "repmixer_dw_kernel", U, 2.0 * Md * c * 58, 3.0 * Md * c * 2);
             if (g_use_fused_mlp && c <= 192) {
                 if ((rc = add_fused_mlp_step(h, pl, U, p, z, y, out, M, c)) != FVHD_OK) return rc;
+            } else if (g_use_cluster_mlp && c == MLPC_C && h->mlpc_clusters > 0) {
+                if ((rc = add_cluster_mlp_step(h, pl, U, p, z, y, out, M)) != FVHD_OK) return rc;
             } else {
                 if ((rc = add_convffn_steps(h, pl, U, p, bf, z, y, out, M, c)) != FVHD_OK) return rc;
             }
@@ -843,7 +901,7 @@ int fvhd_launches_per_forward(fvhd_handle h, int batch) {
     for (const UnitDesc& u : h->units) {
         switch (u.kind) {
         case 0: steps += 2; break;
-        case 1: steps += (g_use_fused_mlp && u.cin <= 192) ? 2 : 3; break;
+        case 1: steps += ((g_use_fused_mlp && u.cin <= 192) || (g_use_cluster_mlp && u.cin == MLPC_C && h->mlpc_clusters > 0)) ? 2 : 3; break;
         case 2: steps += 2; break;
         case 3: steps += 1; break;
         case 4: steps += 7; break;
@@ -1138,5 +1196,29 @@ int fvhd_gemm(fvhd_handle h, void* stream, const void* A, const void* W, const v
     if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "gemm launch failed: %s", cudaGetErrorString(e));
     return FVHD_OK;
 }
+
+int fvhd_convffn(fvhd_handle h, void* stream, const void* z, const void* w1, const void* b1, const void* w2, const void* b2,
+                 const void* resid, void* out, int M, int C, void* trace_64_u64_per_cta) {
+    if (!h) return FVHD_ERR_INVALID;
+    int rc = ensure_cuda(h);
+    if (rc != FVHD_OK) return rc;
+    if (!z || !w1 || !b1 || !w2 || !b2 || !resid || !out || M <= 0) return fail(h, FVHD_ERR_INVALID, "fvhd_convffn: null operand or M <= 0");
+    Step s;
+    if (C == MLPC_C) {
+        rc = make_cluster_mlp_step(h, &s, (const bf16*)z, (const bf16*)w1, (const float*)b1, (const bf16*)w2, (const float*)b2,
+                                   (const bf16*)resid, (bf16*)out, M, (unsigned long long*)trace_64_u64_per_cta);
+    } else if (C == 96 || C == 192) {
+        rc = make_fused_mlp_step(h, &s, (const bf16*)z, (const bf16*)w1, (const float*)b1, (const bf16*)w2, (const float*)b2,
+                                 (const bf16*)resid, (bf16*)out, M, C);
+    } else {
+        return fail(h, FVHD_ERR_INVALID, "fvhd_convffn: fused ConvFFN kernels exist for C in {96, 192, 384}, got %d", C);
+    }
+    if (rc != FVHD_OK) return rc;
+    RunCtx ctx{};
+    cudaError_t e = s(reinterpret_cast<cudaStream_t>(stream), ctx);
+    if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "convffn launch failed: %s", cudaGetErrorString(e));
+    return FVHD_OK;
+}
+
 
 }  // extern "C"

@@ -214,3 +214,14 @@ class Engine:
                                        bias.data_ptr() if bias is not None else None,
                                        residual.data_ptr() if residual is not None else None, D.data_ptr(), M, N, K, int(act)), self.handle)
         return D
+
+    def convffn(self, z, w1, b1, w2, b2, resid, trace=None):
+        """resid + fc2(GELU(fc1(z) + b1)) + b2 on the fused ConvFFN kernels (z, resid [M,C] bf16; w1 [4C,C], w2 [C,4C] bf16;
+        b1, b2 fp32; C in {96, 192, 384}).  `trace`: optional int64 CUDA tensor, 64 entries per CTA (C = 384 only)."""
+        M, Cc = z.shape
+        out = torch.empty(M, Cc, dtype=torch.bfloat16, device=z.device)
+        with torch.cuda.device(z.device):
+            L.check(self.lib.fvhd_convffn(self.handle, C.c_void_p(torch.cuda.current_stream(z.device).cuda_stream), z.data_ptr(), w1.data_ptr(),
+                                          b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), resid.data_ptr(), out.data_ptr(), M, Cc,
+                                          trace.data_ptr() if trace is not None else None), self.handle)
+        return out

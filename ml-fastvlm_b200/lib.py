@@ -51,6 +51,8 @@ SYMBOLS = {
     "fvhd_debug_gemm_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "fvhd_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                             C.c_int, C.c_int, C.c_int, C.c_int]),
+    "fvhd_convffn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_int, C.c_int, C.c_void_p]),
 }
 
 

@@ -249,13 +249,49 @@ def test_fused_convffn_is_bit_identical_to_two_gemms(packed, dev):
     outs = []
     for env_val in ("0", "1"):
         f = tempfile.NamedTemporaryFile(suffix=".pt", delete=False).name
-        env = dict(os.environ, FVHD_NO_FUSED_MLP=env_val)
+        env = dict(os.environ, FVHD_NO_FUSED_MLP=env_val, FVHD_NO_CLUSTER_MLP="1")
         subprocess.run([sys.executable, "-c", code, f], check=True, env=env, timeout=300)
         outs.append(torch.load(f))
         os.unlink(f)
     assert outs[0]["launches"] == outs[1]["launches"] - 14            # 2 + 12 RepMixer blocks lose one launch each
     assert torch.isfinite(outs[0]["p"].float()).all()
     assert torch.equal(outs[0]["t"], outs[1]["t"]) and torch.equal(outs[0]["p"], outs[1]["p"])
+    # stage 2 (C = 384): the 4-CTA-cluster kernel sums four partial accumulators (hidden split across the cluster; the three
+    # remote ones travel as f16) instead of one 24-k-block chain, so it is NOT bit-identical: single-ulp bf16 differences
+    # per block, which this random-weight fixture amplifies ~70x through the remaining depth (tests/golden/sensitivity.json;
+    # the reference's own bf16 run sits 3.8e-2 from its fp32 run).  Bound: two valid bf16 pipelines must agree to that
+    # level; parity of the cluster path itself is checked unit by unit and end to end against the oracle above.
+    f = tempfile.NamedTemporaryFile(suffix=".pt", delete=False).name
+    subprocess.run([sys.executable, "-c", code, f], check=True, env=dict(os.environ, FVHD_NO_FUSED_MLP="0", FVHD_NO_CLUSTER_MLP="0"), timeout=300)
+    clus = torch.load(f)
+    os.unlink(f)
+    assert clus["launches"] == outs[0]["launches"] - 24               # 24 stage-2 blocks lose one launch each
+    assert torch.isfinite(clus["p"].float()).all()
+    dt, dp = rel_l2(clus["t"], outs[0]["t"]), rel_l2(clus["p"], outs[0]["p"])
+    assert dt < 4e-2 and dp < 4e-2, (dt, dp)
+
+
+@pytest.mark.parametrize("C,M", [(96, 128 * 150 + 40), (192, 128 * 9), (384, 4096), (384, 128 * 80 + 128)])
+def test_convffn_kernels_standalone(C, M, dev):
+    """Fused ConvFFN kernels on random operands vs torch (fp32 math on the same bf16 operands, hidden rounded to bf16 as the
+    kernels do): single-CTA kernel for C = 96 / 192 (ragged last tile, several tiles per CTA), 4-CTA-cluster kernel for
+    C = 384 (one tile per cluster, and 81 tiles over <= 37 clusters: the multi-tile path re-uses the DSMEM receive buffer)."""
+    eng = pkg.Engine(64, 0, 2, 1)
+    g = torch.Generator().manual_seed(C + M)
+    z = torch.randn(M, C, generator=g).to(torch.bfloat16).to(dev)
+    resid = torch.randn(M, C, generator=g).to(torch.bfloat16).to(dev)
+    w1 = (torch.randn(4 * C, C, generator=g) / C ** 0.5).to(torch.bfloat16).to(dev)
+    w2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).to(torch.bfloat16).to(dev)
+    b1 = torch.randn(4 * C, generator=g).to(dev)
+    b2 = torch.randn(C, generator=g).to(dev)
+    out = eng.convffn(z, w1, b1, w2, b2, resid)
+    hid = torch.nn.functional.gelu(z.float() @ w1.float().t() + b1).to(torch.bfloat16).float()
+    ref = hid @ w2.float().t() + b2 + resid.float()
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out, ref) < 4e-3                                   # bf16 output rounding (2^-9) + GELU approximation
+    assert (out.float() - ref).abs().max().item() < 0.08
+    again = eng.convffn(z, w1, b1, w2, b2, resid)
+    assert torch.equal(out, again)                                   # deterministic (fixed reduction order)
 
 
 # ------------------------------------------------------------------ drop-in modules
