@@ -144,6 +144,10 @@ int fvhd_resample_coeffs(int in_size, int out_size, int* bounds, int* kk, int kk
  * forced N tile (0 = cost model) and a cluster-size cap (1/2/4).  Process-global; not for production use. */
 int fvhd_debug_gemm_trace(void* dev_buf_16_u64_per_cta, int force_bn, int max_cs);
 
+/* Debug: every RepMixer depthwise launch writes 8 globaltimer stamps per CTA into `dev_buf` (NULL = off); the buffer holds
+ * the most recent launch.  Process-global; not for production use. */
+int fvhd_debug_mixer_trace(void* dev_buf_8_u64_per_cta);
+
 /* Stand-alone GEMM entry (tests): D[M,N] = act(A[M,K] W[N,K]^T + bias) + residual, bf16. */
 int fvhd_gemm(fvhd_handle h, void* stream, const void* A, const void* W, const void* bias, const void* residual,
               void* D, int M, int N, int K, int act);

@@ -27,11 +27,11 @@ template <int V>
 struct OddUp { static constexpr int value = (V & 1) ? V : V + 1; };
 
 // One strip: SW consecutive outputs of one row, one channel pair (-> 2*MULT output channels).
-template <int KS, int S, int MULT, int SW>
+template <int KS, int S, int MULT, int SW, int KYU = KS>
 __device__ __forceinline__ void dw_strip(const uint32_t* __restrict__ tile_row0, int pitch_words,
                                          const float* __restrict__ wsm, int cp, float (&acc)[SW][2 * MULT]) {
     constexpr int NIN = (SW - 1) * S + KS;
-#pragma unroll
+#pragma unroll KYU
     for (int ky = 0; ky < KS; ++ky) {
         const uint32_t* rowp = tile_row0 + ky * pitch_words;
         float2 xin[NIN];
@@ -185,8 +185,13 @@ struct MixCfgT {
     static constexpr size_t SMEM = (size_t)(X_WORDS + Y_WORDS + W_FLOATS) * 4 + 16 /*mbarrier*/;
 };
 
-template <int TOH, int TOW, int NT>
-__global__ void __launch_bounds__(NT, 512 / NT)
+// debug timeline (fvhd_debug_mixer_trace): 8 globaltimer stamps per CTA of the most recent mixer launch
+__device__ unsigned long long* d_mix_trace = nullptr;
+#define MIX_TRACE(i) do { unsigned long long* t_ = d_mix_trace; if (t_) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); \
+    t_[(size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 8 + (i)] = g_; } } while (0)
+
+template <int TOH, int TOW, int NT, int SW1 = 11, int SW2 = 8, int MINB = 512 / NT>
+__global__ void __launch_bounds__(NT, MINB)
 repmixer_dw_kernel(const __grid_constant__ CUtensorMap tmX /*x: NHWC, box {32, XP, XH, 1}*/, bf16* __restrict__ y, bf16* __restrict__ z,
                    const float* __restrict__ w3 /*[9][C]*/, const float* __restrict__ b3,
                    const float* __restrict__ w7 /*[49][C], BN folded*/, const float* __restrict__ b7,
@@ -208,6 +213,7 @@ repmixer_dw_kernel(const __grid_constant__ CUtensorMap tmX /*x: NHWC, box {32, X
     const int tx0 = (blockIdx.x % tiles_x) * TOW;
 
     if (threadIdx.x == 0) {
+        MIX_TRACE(0);
         tma_prefetch_desc(&tmX);
         mbar_init(bar, 1);
         fence_barrier_init();
@@ -220,17 +226,22 @@ repmixer_dw_kernel(const __grid_constant__ CUtensorMap tmX /*x: NHWC, box {32, X
     }
     __syncthreads();                  // barrier initialised, weights staged
     if (threadIdx.x == 0) {
+        MIX_TRACE(1);
         pdl_wait();                   // x is the predecessor's output
+        MIX_TRACE(2);
         mbar_expect_tx(bar, Cfg::X_WORDS * 4);
         tma_load_4d(sx, &tmX, c0, tx0 - 4, ty0 - 4, b, bar);
     }
     mbar_wait(bar, 0);
     pdl_wait();                       // orders this thread's global writes (y, z) after the predecessor
+    if (threadIdx.x == 0) MIX_TRACE(3);
 
     // phase 1: y = dw3x3(x) + b on the (TO+6)^2 region; zero outside the image (the 7x7's zero padding)
     {
-        constexpr int SW = 11, STRIPS = Cfg::YW / SW;
-        static_assert(Cfg::YW % SW == 0 && Cfg::YH % 2 == 0, "phase-1 strip shape");
+        // strips of SW columns; when SW does not divide the region width the last strip is shifted left and recomputes a few
+        // columns of its neighbour (same values, benign duplicate stores)
+        constexpr int SW = SW1, STRIPS = (Cfg::YW + SW - 1) / SW;
+        static_assert(Cfg::YH % 2 == 0 && SW <= Cfg::YW, "phase-1 strip shape");
         constexpr int ITEMS = 16 * Cfg::YH * STRIPS;
         for (int it = threadIdx.x; it < ITEMS; it += NT) {
             const int cp = it & 15;
@@ -239,7 +250,7 @@ repmixer_dw_kernel(const __grid_constant__ CUtensorMap tmX /*x: NHWC, box {32, X
             const int u = t >> 1;
             const int strip = u % STRIPS;
             const int ry = (u / STRIPS) * 2 + sub;            // row in the y region
-            const int rx0 = strip * SW;
+            const int rx0 = (strip * SW + SW <= Cfg::YW) ? strip * SW : Cfg::YW - SW;
             float acc[SW][2];
 #pragma unroll
             for (int j = 0; j < SW; ++j) { acc[j][0] = b3s[cp * 2]; acc[j][1] = b3s[cp * 2 + 1]; }
@@ -259,11 +270,13 @@ repmixer_dw_kernel(const __grid_constant__ CUtensorMap tmX /*x: NHWC, box {32, X
             }
         }
     }
+    if (threadIdx.x == 0) MIX_TRACE(4);
     __syncthreads();
+    if (threadIdx.x == 0) MIX_TRACE(5);
 
     // phase 2: z = dw7x7(y) (BN folded) on the output tile
     {
-        constexpr int SW = 8, STRIPS = TOW / SW;
+        constexpr int SW = SW2, STRIPS = TOW / SW;
         static_assert(TOW % SW == 0 && TOH % 2 == 0, "phase-2 strip shape");
         constexpr int ITEMS = 16 * TOH * STRIPS;
         for (int it = threadIdx.x; it < ITEMS; it += NT) {
@@ -277,7 +290,7 @@ repmixer_dw_kernel(const __grid_constant__ CUtensorMap tmX /*x: NHWC, box {32, X
             float acc[SW][2];
 #pragma unroll
             for (int j = 0; j < SW; ++j) { acc[j][0] = b7s[cp * 2]; acc[j][1] = b7s[cp * 2 + 1]; }
-            dw_strip<7, 1, 1, SW>(sy + (oy * Cfg::YP + ox0) * 16 + cp, Cfg::YP * 16, w7s, cp, acc);
+            dw_strip<7, 1, 1, SW, (MINB * NT > 512 ? 1 : 7)>(sy + (oy * Cfg::YP + ox0) * 16 + cp, Cfg::YP * 16, w7s, cp, acc);
             const int gy = ty0 + oy;
             if (gy >= H) continue;
 #pragma unroll
@@ -288,6 +301,8 @@ repmixer_dw_kernel(const __grid_constant__ CUtensorMap tmX /*x: NHWC, box {32, X
             }
         }
     }
+    if (threadIdx.x == 0) MIX_TRACE(6);
+    if (threadIdx.x == NT - 1) MIX_TRACE(7);
 }
 
 }  // namespace fvhd

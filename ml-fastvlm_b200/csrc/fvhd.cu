@@ -21,6 +21,7 @@
 #include "mlp_cluster.cuh"
 #include "preprocess.cuh"
 #include "stem_attn_se.cuh"
+#include "mixer_tc.cuh"
 
 using namespace fvhd;
 
@@ -341,6 +342,8 @@ int ensure_cuda(fvhd_handle h) {
     }
     CUDA_TRY(h, set_smem(repmixer_dw_kernel<16, 16, 256>, MixCfgT<16, 16>::SMEM));
     CUDA_TRY(h, set_smem(repmixer_dw_kernel<8, 16, 128>, MixCfgT<8, 16>::SMEM));
+    CUDA_TRY(h, set_smem(repmixer_dw_kernel<16, 16, 512, 6, 4, 2>, MixCfgT<16, 16>::SMEM));
+    CUDA_TRY(h, set_smem(repmixer_tc_kernel, MixTc::SMEM));
     CUDA_TRY(h, set_smem(dwconv_kernel<7, 1, 1, 0, 16, 16, 8>, DwCfg<7, 1, 1, 16, 16>::SMEM));
     CUDA_TRY(h, set_smem(dwconv_kernel<7, 2, 2, 1, 8, 8, 4>, DwCfg<7, 2, 2, 8, 8>::SMEM));
     CUDA_TRY(h, set_smem(dwconv_kernel<3, 1, 2, 0, 16, 16, 8>, DwCfg<3, 1, 2, 16, 16>::SMEM));
@@ -608,10 +611,15 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
         }
         case 1: {   // RepMixerBlock: fused dw3x3 -> y, dw7x7(+BN) -> z ; fc1+GELU ; fc2 (+layer scale folded) + y
             const float *w3 = WF(h, p + "mix.w"), *b3 = WF(h, p + "mix.b"), *w7 = WF(h, p + "dw.w"), *b7 = WF(h, p + "dw.b");
-            // tile choice: 16x16 (256 thr) unless that leaves fewer than ~2 CTAs per SM -> 8x16 (128 thr, 4 CTAs/SM)
+            // default: 16x16 tiles with the 7x7 on the tensor cores (mixer_tc.cuh).  FVHD_MIX_TILE selects the FMA-pipe variants
+            // of dwconv.cuh instead: 'a' = their old automatic choice, '1' = 16x16/256 thr, '8' = 8x16/128 thr, '5' = 16x16/512 thr.
             const long ctas16 = (long)((W + 15) / 16) * ((H + 15) / 16) * (c / DW_CG) * batch;
-            bool small = ctas16 < 2L * h->num_sms;
-            { const char* e = getenv("FVHD_MIX_TILE"); if (e && e[0] == '8') small = true; else if (e && e[0] == '1') small = false; }
+            bool small = false, wide = false, tc = true;
+            { const char* e = getenv("FVHD_MIX_TILE");
+              if (e && e[0] == 'a') { tc = false; small = ctas16 < 2L * h->num_sms; }
+              else if (e && e[0] == '8') { tc = false; small = true; }
+              else if (e && e[0] == '1') { tc = false; }
+              else if (e && e[0] == '5') { tc = false; wide = true; } }
             const int TH = small ? 8 : 16;
             const int tx = (W + 15) / 16, ty = (H + TH - 1) / TH;
             const dim3 grid(tx * ty, c / DW_CG, batch);
@@ -619,10 +627,13 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
             CUtensorMap tmx;
             if ((rc = make_tmap_nhwc(h, &tmx, in, batch, H, W, c, small ? MixCfgT<8, 16>::XP : MixCfgT<16, 16>::XP,
                                      small ? MixCfgT<8, 16>::XH : MixCfgT<16, 16>::XH)) != FVHD_OK) return rc;
+            static_assert(MixTc::XP == MixCfgT<16, 16>::XP && MixTc::XH == MixCfgT<16, 16>::XH, "same TMA box for both 16x16 kernels");
             pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+                if (tc) return launch_k(repmixer_tc_kernel, grid, dim3(MixTc::NT), MixTc::SMEM, s, tmx, y, z, w3, b3, w7, b7, H, W, c, tx);
+                if (wide) return launch_k(repmixer_dw_kernel<16, 16, 512, 6, 4, 2>, grid, dim3(512), MixCfgT<16, 16>::SMEM, s, tmx, y, z, w3, b3, w7, b7, H, W, c, tx);
                 if (small) return launch_k(repmixer_dw_kernel<8, 16, 128>, grid, dim3(128), MixCfgT<8, 16>::SMEM, s, tmx, y, z, w3, b3, w7, b7, H, W, c, tx);
                 return launch_k(repmixer_dw_kernel<16, 16, 256>, grid, dim3(256), MixCfgT<16, 16>::SMEM, s, tmx, y, z, w3, b3, w7, b7, H, W, c, tx);
-            }, "repmixer_dw_kernel", U, 2.0 * Md * c * 58, 3.0 * Md * c * 2);
+            }, tc ? "repmixer_tc_kernel" : "repmixer_dw_kernel", U, 2.0 * Md * c * 58, 3.0 * Md * c * 2);
             if (g_use_fused_mlp && c <= 192) {
                 if ((rc = add_fused_mlp_step(h, pl, U, p, z, y, out, M, c)) != FVHD_OK) return rc;
             } else if (g_use_cluster_mlp && c == MLPC_C && h->mlpc_clusters > 0) {
@@ -1182,6 +1193,11 @@ int fvhd_debug_gemm_trace(void* dev_buf_16_u64_per_cta, int force_bn, int max_cs
     g_force_bn = force_bn;
     if (max_cs == 1 || max_cs == 2 || max_cs == 4) g_gemm_max_cs = max_cs;
     return FVHD_OK;
+}
+
+int fvhd_debug_mixer_trace(void* dev_buf_8_u64_per_cta) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(dev_buf_8_u64_per_cta);
+    return cudaMemcpyToSymbol(d_mix_trace, &p, sizeof(p)) == cudaSuccess ? FVHD_OK : FVHD_ERR_CUDA;
 }
 
 int fvhd_gemm(fvhd_handle h, void* stream, const void* A, const void* W, const void* bias, const void* residual, void* D, int M, int N, int K, int act) {

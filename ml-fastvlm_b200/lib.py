@@ -49,6 +49,7 @@ SYMBOLS = {
     "fvhd_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "fvhd_resample_coeffs": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]),
     "fvhd_debug_gemm_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "fvhd_debug_mixer_trace": (C.c_int, [C.c_void_p]),
     "fvhd_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                             C.c_int, C.c_int, C.c_int, C.c_int]),
     "fvhd_convffn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
