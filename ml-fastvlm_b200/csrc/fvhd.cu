@@ -636,7 +636,9 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
             }, tc ? "repmixer_tc_kernel" : "repmixer_dw_kernel", U, 2.0 * Md * c * 58, 3.0 * Md * c * 2);
             if (g_use_fused_mlp && c <= 192) {
                 if ((rc = add_fused_mlp_step(h, pl, U, p, z, y, out, M, c)) != FVHD_OK) return rc;
-            } else if (g_use_cluster_mlp && c == MLPC_C && h->mlpc_clusters > 0) {
+            } else if (g_use_cluster_mlp && c == MLPC_C && h->mlpc_clusters > 0 && (M + GEMM_BM - 1) / GEMM_BM <= 2 * h->mlpc_clusters) {
+                // small batches only: beyond two tiles per resident cluster the two plain GEMMs fill the machine better
+                // (measured: batch 1 0.71 vs 0.91 ms for the 24 blocks, batch 4 2.23 vs 2.15 ms, batch 8 4.28 vs 3.67 ms)
                 if ((rc = add_cluster_mlp_step(h, pl, U, p, z, y, out, M)) != FVHD_OK) return rc;
             } else {
                 if ((rc = add_convffn_steps(h, pl, U, p, bf, z, y, out, M, c)) != FVHD_OK) return rc;
@@ -908,11 +910,17 @@ int fvhd_unit_info(fvhd_handle h, int u, const char** name, int64_t* in_elems, i
 int fvhd_launches_per_forward(fvhd_handle h, int batch) {
     if (!h) return FVHD_ERR_INVALID;
     // steps per pass, + 2 for the three-kernel SE step, x number of passes
+    const int batch_per_pass = batch < h->cfg.max_batch ? batch : h->cfg.max_batch;
     int steps = 0;
     for (const UnitDesc& u : h->units) {
         switch (u.kind) {
         case 0: steps += 2; break;
-        case 1: steps += ((g_use_fused_mlp && u.cin <= 192) || (g_use_cluster_mlp && u.cin == MLPC_C && h->mlpc_clusters > 0)) ? 2 : 3; break;
+        case 1: {
+            const int tiles_m = (batch_per_pass * u.hout * u.wout + GEMM_BM - 1) / GEMM_BM;
+            steps += ((g_use_fused_mlp && u.cin <= 192) ||
+                      (g_use_cluster_mlp && u.cin == MLPC_C && h->mlpc_clusters > 0 && tiles_m <= 2 * h->mlpc_clusters)) ? 2 : 3;
+            break;
+        }
         case 2: steps += 2; break;
         case 3: steps += 1; break;
         case 4: steps += 7; break;
