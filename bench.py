@@ -261,8 +261,9 @@ def run_gpu_arm(args):
             ktab.append({"kernel": name, "launches": k["launches"], "ms": round(k["ms"], 4), "share": round(k["ms"] / sum(ms), 4),
                          "tflops": round(k["flops"] / k["ms"] / 1e9, 1) if k["ms"] > 0 else None,
                          "gbs": round(k["bytes"] / k["ms"] / 1e6, 1) if k["ms"] > 0 else None})
-        # the tensor-pipe kernels: the tcgen05 GEMM and the fused ConvFFN (fc1 -> GELU -> fc2 in one kernel)
-        tc_names = [n for n in ("gemm_bf16_tcgen05_kernel", "mlp_fused_tcgen05_kernel") if n in kernels]
+        # the tensor-pipe kernels: the tcgen05 GEMM and the fused ConvFFN kernels (fc1 -> GELU -> fc2 in one launch; single CTA
+        # per tile for C <= 192, a 4-CTA cluster per tile for C = 384)
+        tc_names = [n for n in ("gemm_bf16_tcgen05_kernel", "mlp_cluster_tcgen05_kernel", "mlp_fused_tcgen05_kernel") if n in kernels]
         gk = {"launches": sum(kernels[n]["launches"] for n in tc_names), "ms": sum(kernels[n]["ms"] for n in tc_names),
               "flops": sum(kernels[n]["flops"] for n in tc_names), "bytes": sum(kernels[n]["bytes"] for n in tc_names)}
         ach = gk["flops"] / gk["ms"] / 1e9           # TFLOP/s

@@ -11,16 +11,20 @@
 //       epi1  acc1 -> +b1 -> GELU -> bf16 -> H[j&1] (smem, K-major SW128)
 //       MMA2  acc2 (TMEM 384 cols)     += H[j&1] . W2[:, 384 r + 64 j ..]^T  (two N = 192 halves, one slot each)
 //
-// and the four partial fc2 accumulators (fp32, TMEM) are reduced THROUGH DISTRIBUTED SHARED MEMORY: CTA q owns output
-// columns [96 q, 96 q + 96); every CTA stores its partial of those columns into q's receive buffer (st.shared::cluster,
-// overlaid on the then-dead z / H / W smem), q adds its own partial, b2 and the residual and stores bf16.
-// Per CTA this moves 96 KB (z) + 2 x 288 KB (W1, W2 slices) through TMA and 144 KB through DSMEM, instead of the two
-// GEMM launches' 196 KB / 786 KB per tile over 3.6 / 1 waves -- and the 12.6 MB hidden never exists.
+// and the four partial fc2 accumulators (fp32, TMEM) are reduce-scattered THROUGH DISTRIBUTED SHARED MEMORY: CTA q owns output
+// columns [96 q, 96 q + 96); every CTA converts its partial of a peer's columns to f16 (saturating), stages it in the layout the
+// receiver reads ([8-column group][row] x 16 B, overlaid on the then-dead z / H smem) and sends it with ONE 24-KB
+// cp.async.bulk.shared::cluster per peer that completes on the peer's mbarrier; q then adds its own fp32 partial, the three
+// received ones, b2 and the residual and stores bf16.  Per CTA this moves 96 KB (z) + 2 x 288 KB (W1, W2 slices) through TMA and
+// 72 KB each way through DSMEM, instead of the two GEMM launches' 196 KB / 786 KB per tile over 2.6 / 1 waves -- and the
+// 12.6 MB hidden never exists.  (fp32 partials over st.shared::cluster + fence.acq_rel.cluster were measured first: 9.7 us of
+// reduction tail against 6.1 us for this scheme; the DSMEM path itself moves ~13 B/clk per SM.)
 //
 // Synchronisation across the cluster uses mbarriers with remote arrives only (no barrier.cluster after start-up, so the
 // single-lane TMA / MMA warps never have to take part):
-//   ready_bar (count 4): "CTA x has retired all its MMAs of this tile" -> x's smem may be overwritten by its peers
-//   recv_bar  (count 3 peers x 8 warps): "all partials for my columns have landed"
+//   ready_bar (count 4, remote arrives): "CTA x has retired all its MMAs of this tile" -> x's smem may be overwritten
+//   recv_bar  (count 1 + 72 KB of complete_tx): own expect_tx + the three peers' bulk copies have landed
+//   ack_bar   (count 3, remote arrives): the peers have received what this CTA staged -> staging may be recycled / CTA may exit
 //   tile_done (count 8 warps, local): receive buffer consumed -> the producer may load the next tile's z / W
 #pragma once
 #include "mlp_fused.cuh"
