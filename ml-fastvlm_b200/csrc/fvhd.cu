@@ -550,7 +550,6 @@ int make_cluster_mlp_step(fvhd_handle h, Step* st, const bf16* z, const bf16* w1
     MlpParams mp{};
     mp.M = M; mp.C = c; mp.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
     mp.b1 = b1; mp.b2 = b2; mp.resid = resid; mp.D = out; mp.trace = trace;
-    { const char* e = getenv("FVHD_MLP_STAGGER"); mp.stagger = (e && e[0] == '1') ? 1 : 0; }
     CUtensorMap tz, tw1, tw2;
     int rc;
     if ((rc = make_tmap(h, &tz, z, M, c, c, GEMM_BM)) != FVHD_OK) return rc;

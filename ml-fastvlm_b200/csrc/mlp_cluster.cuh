@@ -140,19 +140,17 @@ mlp_cluster_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid
             };
             int ti = 0;
             for (int tile = cluster_id; tile < p.tiles_m; tile += num_clusters, ++ti) {
-                const int rot = p.stagger ? tile % MLPC_NC : 0;                    // chunk visited at step j: (j + rot) % NC
-                auto cj = [&](int j) { const int x = j + rot; return x >= MLPC_NC ? x - MLPC_NC : x; };
                 mbar_wait(tile_done, ((uint32_t)ti & 1u) ^ 1u);                   // previous tile's receive buffer (z overlay) consumed ...
                 mbar_wait_cluster(ack_bar, ((uint32_t)ti & 1u) ^ 1u);             // ... and its staged partials fetched by the peers
                 MLPC_TRACE(2);
                 mbar_expect_tx(z_full, MLPC_Z_BYTES);
                 for (int kb = 0; kb < MLPC_KB; ++kb) tma_load_2d(smemZ + (size_t)kb * GEMM_A_STAGE_BYTES, &tmZ, kb * 64, tile * GEMM_BM, z_full);
-                load_w(false, cj(0), 0); load_w(false, cj(0), 1);
+                load_w(false, 0, 0); load_w(false, 0, 1);
                 for (int j = 1; j < MLPC_NC; ++j) {
-                    load_w(false, cj(j), 0); load_w(false, cj(j), 1);
-                    load_w(true, cj(j - 1), 0); load_w(true, cj(j - 1), 1);
+                    load_w(false, j, 0); load_w(false, j, 1);
+                    load_w(true, j - 1, 0); load_w(true, j - 1, 1);
                 }
-                load_w(true, cj(MLPC_NC - 1), 0); load_w(true, cj(MLPC_NC - 1), 1);
+                load_w(true, MLPC_NC - 1, 0); load_w(true, MLPC_NC - 1, 1);
             }
         }
     } else if (warp == 1) {
@@ -233,9 +231,7 @@ mlp_cluster_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid
             for (int j = 0; j < MLPC_NC; ++j) {
                 const int b = j & 1;
                 const uint32_t use = (uint32_t)(ti * half_nc + (j >> 1));
-                int jc = j + (p.stagger ? tile % MLPC_NC : 0);
-                jc = jc >= MLPC_NC ? jc - MLPC_NC : jc;                            // the producer's chunk rotation
-                const float4* bb = reinterpret_cast<const float4*>(p.b1 + hid0 + jc * MLP_NH + hh * 32);
+                const float4* bb = reinterpret_cast<const float4*>(p.b1 + hid0 + j * MLP_NH + hh * 32);
                 float4 bv[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) bv[i] = __ldg(bb + i);                // constants: issued before the wait

@@ -30,7 +30,6 @@ struct MlpParams {
     const bf16* resid;         // [M, C]
     bf16* D;                   // [M, C]
     unsigned long long* trace; // cluster kernel, debug: 64 globaltimer stamps per CTA (nullptr = off)
-    int stagger;               // cluster kernel: rotate the hidden-chunk order per tile (de-synchronises the weight streams)
 };
 
 __host__ __device__ inline int mlp_kb(int C) { return (C + 63) / 64; }
