@@ -136,6 +136,12 @@ int fvhd_launches_per_forward(fvhd_handle h, int batch);
  *   out   device, [3, R, R] of out_dtype (one image of the tower's input batch) */
 int fvhd_preprocess(fvhd_handle h, void* stream, const void* rgb, int src_on_host, int H, int W, int pad_to_square,
                     void* out, int out_dtype);
+/* 'anyres' building block (llava/mm_utils.py:46-98, 121-147: resize_and_pad_image + divide_to_patches + processor.preprocess):
+ * PIL-resize the image to new_h x new_w (BICUBIC, bit-exact), paste it at (pad_y, pad_x) on a black canvas and emit the canvas as
+ * tiles_y x tiles_x row-major tiles of R x R (pixels beyond the pasted image are 0), x 1/255.  out: device, [tiles_y*tiles_x, 3, R, R].
+ * The global view of process_anyres_image is the call new_h = new_w = R, pad 0, one tile. */
+int fvhd_preprocess_tiles(fvhd_handle h, void* stream, const void* rgb, int src_on_host, int H, int W, int new_h, int new_w,
+                          int pad_y, int pad_x, int tiles_y, int tiles_x, void* out, int out_dtype);
 /* Host-only: Pillow's fixed-point bicubic coefficient table for resampling in_size -> out_size (Resample.c precompute_coeffs +
  * normalize_coeffs_8bpc).  bounds [out][2] = (first source index, tap count); kk [out][ksize]; returns ksize (or < 0). */
 int fvhd_resample_coeffs(int in_size, int out_size, int* bounds, int* kk, int kk_capacity);

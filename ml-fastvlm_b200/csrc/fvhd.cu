@@ -1134,22 +1134,13 @@ static int rs_get_table(fvhd_handle h, int in_size, int out_size, fvhd_handle_s:
     return FVHD_OK;
 }
 
-int fvhd_preprocess(fvhd_handle h, void* stream, const void* rgb, int src_on_host, int H, int W, int pad_to_square, void* out, int out_dtype) {
-    if (!h) return FVHD_ERR_INVALID;
-    int rc = ensure_cuda(h);
-    if (rc != FVHD_OK) return rc;
-    if (!rgb || !out || H < 1 || W < 1) return fail(h, FVHD_ERR_INVALID, "fvhd_preprocess: bad image %dx%d", H, W);
-    if (out_dtype < FVHD_F32 || out_dtype > FVHD_BF16) return fail(h, FVHD_ERR_INVALID, "fvhd_preprocess: bad output dtype %d", out_dtype);
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+// Shared body of the preprocessing entries: the image (H x W u8 RGB, optionally centred on an Hs x Ws black canvas BEFORE the
+// resize = expand2square) is PIL-resized to oh x ow; the result is shown through tiles_y x tiles_x windows of R x R whose first
+// one starts at (top, left) of the resized image (pixels outside it are black), x 1/255, NCHW.
+static int preprocess_impl(fvhd_handle h, cudaStream_t st, const void* rgb, int src_on_host, int H, int W, int Hs, int Ws, int offy, int offx,
+                           int oh, int ow, int top, int left, int tiles_y, int tiles_x, void* out, int out_dtype) {
+    int rc;
     const int R = h->R;
-    // expand2square (mm_utils.py:154-165): canvas Hs x Ws with the image at (offy, offx)
-    const int Hs = pad_to_square ? (H > W ? H : W) : H, Ws = pad_to_square ? Hs : W;
-    const int offy = pad_to_square && W > H ? (W - H) / 2 : 0, offx = pad_to_square && H > W ? (H - W) / 2 : 0;
-    // get_resize_output_image_size(size = R, default_to_square = False)
-    const int shortE = Ws <= Hs ? Ws : Hs, longE = Ws <= Hs ? Hs : Ws;
-    const int new_long = (int)((double)R * longE / shortE);
-    const int oh = Ws <= Hs ? new_long : R, ow = Ws <= Hs ? R : new_long;
-    const int top = (oh - R) / 2, left = (ow - R) / 2;
     if (!h->rs_lut) {
         float lut[256];
         for (int i = 0; i < 256; ++i) lut[i] = (float)((double)i * (1.0 / 255.0));      // transformers rescale(): float64 multiply
@@ -1187,12 +1178,42 @@ int fvhd_preprocess(fvhd_handle h, void* stream, const void* rgb, int src_on_hos
     if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "preprocess horizontal pass: %s", cudaGetErrorString(e));
     // vertical pass (identity table when oh == Hs: one tap of weight 1 << 22 -> exact copy)
     if ((rc = rs_get_table(h, Hs, oh, &ty)) != FVHD_OK) return rc;
-    const dim3 g2((R + 127) / 128, R);
-    if (out_dtype == FVHD_F32) e = launch_k(resample_v_crop_kernel<float>, g2, dim3(128), 0, st, (const uint8_t*)h->rs_tmp, ow, (float*)out, R, top, left, (const int*)ty.bounds, (const int*)ty.kk, ty.ksize, (const float*)h->rs_lut);
-    else if (out_dtype == FVHD_F16) e = launch_k(resample_v_crop_kernel<__half>, g2, dim3(128), 0, st, (const uint8_t*)h->rs_tmp, ow, (__half*)out, R, top, left, (const int*)ty.bounds, (const int*)ty.kk, ty.ksize, (const float*)h->rs_lut);
-    else e = launch_k(resample_v_crop_kernel<bf16>, g2, dim3(128), 0, st, (const uint8_t*)h->rs_tmp, ow, (bf16*)out, R, top, left, (const int*)ty.bounds, (const int*)ty.kk, ty.ksize, (const float*)h->rs_lut);
+    const dim3 g2((R + 127) / 128, R, tiles_y * tiles_x);
+    if (out_dtype == FVHD_F32) e = launch_k(resample_v_crop_kernel<float>, g2, dim3(128), 0, st, (const uint8_t*)h->rs_tmp, ow, oh, (float*)out, R, top, left, tiles_x, (const int*)ty.bounds, (const int*)ty.kk, ty.ksize, (const float*)h->rs_lut);
+    else if (out_dtype == FVHD_F16) e = launch_k(resample_v_crop_kernel<__half>, g2, dim3(128), 0, st, (const uint8_t*)h->rs_tmp, ow, oh, (__half*)out, R, top, left, tiles_x, (const int*)ty.bounds, (const int*)ty.kk, ty.ksize, (const float*)h->rs_lut);
+    else e = launch_k(resample_v_crop_kernel<bf16>, g2, dim3(128), 0, st, (const uint8_t*)h->rs_tmp, ow, oh, (bf16*)out, R, top, left, tiles_x, (const int*)ty.bounds, (const int*)ty.kk, ty.ksize, (const float*)h->rs_lut);
     if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "preprocess vertical pass: %s", cudaGetErrorString(e));
     return FVHD_OK;
+}
+
+int fvhd_preprocess(fvhd_handle h, void* stream, const void* rgb, int src_on_host, int H, int W, int pad_to_square, void* out, int out_dtype) {
+    if (!h) return FVHD_ERR_INVALID;
+    int rc = ensure_cuda(h);
+    if (rc != FVHD_OK) return rc;
+    if (!rgb || !out || H < 1 || W < 1) return fail(h, FVHD_ERR_INVALID, "fvhd_preprocess: bad image %dx%d", H, W);
+    if (out_dtype < FVHD_F32 || out_dtype > FVHD_BF16) return fail(h, FVHD_ERR_INVALID, "fvhd_preprocess: bad output dtype %d", out_dtype);
+    const int R = h->R;
+    // expand2square (mm_utils.py:154-165): canvas Hs x Ws with the image at (offy, offx)
+    const int Hs = pad_to_square ? (H > W ? H : W) : H, Ws = pad_to_square ? Hs : W;
+    const int offy = pad_to_square && W > H ? (W - H) / 2 : 0, offx = pad_to_square && H > W ? (H - W) / 2 : 0;
+    // get_resize_output_image_size(size = R, default_to_square = False)
+    const int shortE = Ws <= Hs ? Ws : Hs, longE = Ws <= Hs ? Hs : Ws;
+    const int new_long = (int)((double)R * longE / shortE);
+    const int oh = Ws <= Hs ? new_long : R, ow = Ws <= Hs ? R : new_long;
+    const int top = (oh - R) / 2, left = (ow - R) / 2;
+    return preprocess_impl(h, reinterpret_cast<cudaStream_t>(stream), rgb, src_on_host, H, W, Hs, Ws, offy, offx, oh, ow, top, left, 1, 1, out, out_dtype);
+}
+
+int fvhd_preprocess_tiles(fvhd_handle h, void* stream, const void* rgb, int src_on_host, int H, int W, int new_h, int new_w,
+                          int pad_y, int pad_x, int tiles_y, int tiles_x, void* out, int out_dtype) {
+    if (!h) return FVHD_ERR_INVALID;
+    int rc = ensure_cuda(h);
+    if (rc != FVHD_OK) return rc;
+    if (!rgb || !out || H < 1 || W < 1 || new_h < 1 || new_w < 1 || tiles_y < 1 || tiles_x < 1 || pad_y < 0 || pad_x < 0)
+        return fail(h, FVHD_ERR_INVALID, "fvhd_preprocess_tiles: bad geometry %dx%d -> %dx%d, pad (%d,%d), tiles %dx%d", H, W, new_h, new_w, pad_y, pad_x, tiles_y, tiles_x);
+    if (out_dtype < FVHD_F32 || out_dtype > FVHD_BF16) return fail(h, FVHD_ERR_INVALID, "fvhd_preprocess_tiles: bad output dtype %d", out_dtype);
+    // the canvas pixel (y, x) shows resized-image pixel (y - pad_y, x - pad_x): the first tile starts at (-pad_y, -pad_x)
+    return preprocess_impl(h, reinterpret_cast<cudaStream_t>(stream), rgb, src_on_host, H, W, H, W, 0, 0, new_h, new_w, -pad_y, -pad_x, tiles_y, tiles_x, out, out_dtype);
 }
 
 int fvhd_debug_gemm_trace(void* dev_buf_16_u64_per_cta, int force_bn, int max_cs) {

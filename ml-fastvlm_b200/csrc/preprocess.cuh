@@ -2,7 +2,8 @@
 //
 // Reference: llava/mm_utils.py:168-184 (process_images) -> CLIPImageProcessor of the pinned transformers 4.48.3, configured by
 // mobileclip_encoder.py:45-49: resize shortest edge to R with PIL BICUBIC -> centre crop R x R -> x 1/255 -> (mean 0, std 1)
-// -> CHW.  'pad' mode pastes the image centred on a zero square first (expand2square, mm_utils.py:154-165).
+// -> CHW.  'pad' mode pastes the image centred on a zero square first (expand2square, mm_utils.py:154-165); 'anyres'
+// (process_anyres_image, mm_utils.py:121-147) resizes to a computed size, pastes on a black best-fit canvas and cuts R x R tiles.
 // The arithmetic is Pillow's 8-bit separable resampler (src/libImaging/Resample.c): horizontal pass, uint8 intermediate,
 // vertical pass, coefficients in 22-bit fixed point.  The tables are computed on the host with the same double arithmetic
 // (resample_coeffs below), the passes are HBM-bound byte kernels: one thread per output pixel (3 channels), int32 accumulate.
@@ -102,31 +103,38 @@ template <> __device__ __forceinline__ float rs_cast<float>(float v) { return v;
 template <> __device__ __forceinline__ __half rs_cast<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ bf16 rs_cast<bf16>(float v) { return __float2bfloat16_rn(v); }
 
-// Vertical pass + centre crop + x 1/255 (256-entry LUT, computed in double on the host) + NCHW store.
-// tmp [Hs, ow, 3] u8 -> out [3, R, R] of T.  grid (ceil(R/128), R), 128 threads.
+// Vertical pass + window + x 1/255 (256-entry LUT, computed in double on the host) + NCHW store.
+// tmp [Hs, ow, 3] u8 (rows of the horizontally resized image) -> out [tiles, 3, R, R] of T.  Tile t = (ty, tx) = (t / tiles_x,
+// t % tiles_x) shows rows [top + ty R, +R) x cols [left + tx R, +R) of the vertically resized image (oh x ow); pixels outside
+// it are 0 (the black canvas of 'pad' / 'anyres').  The plain centre crop is one tile with top, left >= 0 inside the image.
+// grid (ceil(R/128), R, tiles), 128 threads.
 template <typename T>
 __global__ void __launch_bounds__(128)
-resample_v_crop_kernel(const uint8_t* __restrict__ tmp, int ow, T* __restrict__ out, int R, int top, int left,
+resample_v_crop_kernel(const uint8_t* __restrict__ tmp, int ow, int oh, T* __restrict__ out, int R, int top, int left, int tiles_x,
                        const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, const float* __restrict__ lut) {
     pdl_launch_dependents();
     pdl_wait();
     const int xo = blockIdx.x * 128 + threadIdx.x;
     const int yo = blockIdx.y;
     if (xo >= R) return;
-    const int yy = yo + top, xx = xo + left;
-    const int ymin = bounds[2 * yy], cnt = bounds[2 * yy + 1];
-    const int* kp = kk + (size_t)yy * ksize;
-    int a0 = 1 << (RS_PRECISION_BITS - 1), a1 = a0, a2 = a0;
-    for (int k = 0; k < cnt; ++k) {
-        const uint8_t* p = tmp + ((size_t)(ymin + k) * ow + xx) * 3;
-        const int c = kp[k];
-        a0 += p[0] * c; a1 += p[1] * c; a2 += p[2] * c;
+    const int t = blockIdx.z;
+    const int yy = yo + top + (t / tiles_x) * R, xx = xo + left + (t % tiles_x) * R;
+    int a0 = 0, a1 = 0, a2 = 0;                                  // outside the image: black
+    if (yy >= 0 && yy < oh && xx >= 0 && xx < ow) {
+        const int ymin = bounds[2 * yy], cnt = bounds[2 * yy + 1];
+        const int* kp = kk + (size_t)yy * ksize;
+        a0 = a1 = a2 = 1 << (RS_PRECISION_BITS - 1);
+        for (int k = 0; k < cnt; ++k) {
+            const uint8_t* p = tmp + ((size_t)(ymin + k) * ow + xx) * 3;
+            const int c = kp[k];
+            a0 += p[0] * c; a1 += p[1] * c; a2 += p[2] * c;
+        }
     }
     const size_t plane = (size_t)R * R;
-    const size_t o = (size_t)yo * R + xo;
-    out[o] = rs_cast<T>(__ldg(lut + rs_clip8(a0)));
-    out[plane + o] = rs_cast<T>(__ldg(lut + rs_clip8(a1)));
-    out[2 * plane + o] = rs_cast<T>(__ldg(lut + rs_clip8(a2)));
+    T* o = out + (size_t)t * 3 * plane + (size_t)yo * R + xo;
+    o[0] = rs_cast<T>(__ldg(lut + rs_clip8(a0)));
+    o[plane] = rs_cast<T>(__ldg(lut + rs_clip8(a1)));
+    o[2 * plane] = rs_cast<T>(__ldg(lut + rs_clip8(a2)));
 }
 
 // No resampling needed along an axis (out == in): PIL skips that pass.  Copy kernels keep the code path uniform.

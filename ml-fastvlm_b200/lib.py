@@ -47,6 +47,8 @@ SYMBOLS = {
     "fvhd_profile_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int]),
     "fvhd_launches_per_forward": (C.c_int, [C.c_void_p, C.c_int]),
     "fvhd_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "fvhd_preprocess_tiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_int]),
     "fvhd_resample_coeffs": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]),
     "fvhd_debug_gemm_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "fvhd_debug_mixer_trace": (C.c_int, [C.c_void_p]),

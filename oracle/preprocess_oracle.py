@@ -121,3 +121,49 @@ def preprocess(img, res, pad=False):
     top, left = (oh - res) // 2, (ow - res) // 2
     x = x[top:top + res, left:left + res, :]
     return np.ascontiguousarray(RESCALE_LUT[x].transpose(2, 0, 1))
+
+
+# ------------------------------------------------------------------ image_aspect_ratio == "anyres"
+def select_best_resolution(original_size, possible_resolutions):
+    """mm_utils.py:14-43.  original_size = (width, height); returns the (width, height) pin that keeps the most pixels of the
+    aspect-preserving downscale and, among those, wastes the least canvas."""
+    ow, oh = original_size
+    best, max_eff, min_waste = None, 0, float("inf")
+    for w, h in possible_resolutions:
+        scale = min(w / ow, h / oh)
+        dw, dh = int(ow * scale), int(oh * scale)
+        eff = min(dw * dh, ow * oh)
+        waste = w * h - eff
+        if eff > max_eff or (eff == max_eff and waste < min_waste):
+            max_eff, min_waste, best = eff, waste, (w, h)
+    return best
+
+
+def anyres_geometry(w, h, grid_pinpoints):
+    """mm_utils.py:46-76 (resize_and_pad_image) without the pixels: canvas (cw, ch), resized size (nw, nh), paste offset (px, py)."""
+    import math
+    cw, ch = select_best_resolution((w, h), [tuple(p) for p in grid_pinpoints])
+    sw, sh = cw / w, ch / h
+    if sw < sh:
+        nw, nh = cw, min(math.ceil(h * sw), ch)
+    else:
+        nh, nw = ch, min(math.ceil(w * sh), cw)
+    return cw, ch, nw, nh, (cw - nw) // 2, (ch - nh) // 2
+
+
+def preprocess_anyres(img, res, grid_pinpoints):
+    """mm_utils.py:121-147 (process_anyres_image) for the FastVLM processor (crop = shortest_edge = res, mean 0, std 1):
+    [global view resized to res x res] + [res x res patches of the resized image pasted on the black best-fit canvas], each
+    x 1/255 -> float32 [1 + n, 3, res, res].  Patches already have the processor's size, so its resize / crop are no-ops."""
+    h, w, _ = img.shape
+    cw, ch, nw, nh, px, py = anyres_geometry(w, h, grid_pinpoints)
+    canvas = np.zeros((ch, cw, 3), dtype=np.uint8)
+    canvas[py:py + nh, px:px + nw] = resize_bicubic_u8(img, nw, nh)
+    views = [resize_bicubic_u8(img, res, res)]
+    for i in range(0, ch, res):
+        for j in range(0, cw, res):
+            patch = np.zeros((res, res, 3), dtype=np.uint8)          # PIL crop beyond the canvas pads with black
+            sub = canvas[i:i + res, j:j + res]
+            patch[:sub.shape[0], :sub.shape[1]] = sub
+            views.append(patch)
+    return np.ascontiguousarray(RESCALE_LUT[np.stack(views)].transpose(0, 3, 1, 2))

@@ -88,3 +88,53 @@ def test_gpu_process_images_feeds_the_tower(tower_sd):
     assert torch.equal(x.cpu(), want)
     feats = tower(x)
     assert tuple(feats.shape) == (2, 16, 3072) and torch.isfinite(feats.float()).all()
+
+
+# ------------------------------------------------------------------ image_aspect_ratio == "anyres" (mm_utils.py:14-147)
+def _anyres_cases():
+    import json
+    import os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    cases = json.load(open(os.path.join(gdir, "anyres_cases.json")))
+    gold = np.load(os.path.join(gdir, "anyres_ref.npz"))
+    return [(h, w, R, [tuple(p) for p in pins], seed, gold[f"case{i}"], tuple(int(v) for v in gold[f"grid{i}"]))
+            for i, (h, w, R, pins, seed) in enumerate(cases)]
+
+
+def test_anyres_oracle_matches_reference_golden():
+    """tests/golden/anyres_ref.npz was produced by the unmodified reference (oracle/gen_golden_anyres.py): global view + tiles,
+    including a canvas that is not a multiple of the patch size.  The numpy restatement must reproduce it bit for bit, and the
+    host-side geometry helpers must agree with the reference's get_anyres_image_grid_shape."""
+    for h, w, R, pins, seed, k, grid in _anyres_cases():
+        img = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        got = po.preprocess_anyres(img, R, pins)
+        assert got.shape == k.shape and got.dtype == np.float32
+        assert np.array_equal(got, po.RESCALE_LUT[k])
+        assert pkg.get_anyres_image_grid_shape((w, h), pins, R) == grid == pkg.get_anyres_image_grid_shape((w, h), str(pins), R)
+        assert pkg.select_best_resolution((w, h), pins) == po.select_best_resolution((w, h), pins)
+
+
+@pytest.mark.gpu
+def test_gpu_anyres_bit_exact():
+    dev = torch.device("cuda:0")
+    for h, w, R, pins, seed, k, grid in _anyres_cases():
+        eng = pkg.Engine(R, 0, 2, 1)
+        eng.device = dev                                   # preprocessing needs no weights
+        img = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = torch.from_numpy(po.RESCALE_LUT[k])         # the reference's own output
+        out = pkg.process_anyres_image(img, eng, pins, torch.float32)
+        assert tuple(out.shape) == tuple(want.shape) and torch.equal(out.cpu(), want)
+        out16 = pkg.process_anyres_image(torch.from_numpy(img).to(dev), eng, str(pins), torch.float16)      # device source, str pins
+        assert torch.equal(out16.cpu(), want.half())
+
+    class Cfg:
+        image_aspect_ratio = "anyres"
+        image_grid_pinpoints = [(64, 128), (128, 64), (128, 128)]
+    eng = pkg.Engine(64, 0, 2, 1)
+    eng.device = dev
+    imgs = [np.random.default_rng(s).integers(0, 256, (100, 150, 3), dtype=np.uint8) for s in (1, 2)]
+    x = pkg.process_images(imgs, eng, Cfg(), dtype=torch.float32)
+    wants = [torch.from_numpy(po.preprocess_anyres(im, 64, Cfg.image_grid_pinpoints)) for im in imgs]
+    assert tuple(x.shape) == (2,) + tuple(wants[0].shape) == (2, 5, 3, 64, 64)     # same tile count -> stacked, as the reference does
+    for i in range(2):
+        assert torch.equal(x[i].cpu(), wants[i])
