@@ -89,16 +89,14 @@ def process_anyres_image(image, engine, grid_pinpoints, dtype=torch.float16):
     dev = engine.device
     out = torch.empty(1 + ty * tx, 3, R, R, dtype=dtype, device=dev)
     with torch.cuda.device(dev):
+        if not t.is_cuda:                                              # one upload (3 B/pixel) serves both calls
+            t = (t if t.is_pinned() else t.pin_memory()).to(dev, non_blocking=True)
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        on_host = 0 if t.is_cuda else 1
-        if on_host and not t.is_pinned():
-            t = t.pin_memory()
-        L.check(engine.lib.fvhd_preprocess_tiles(engine.handle, stream, t.data_ptr(), on_host, H, W, R, R, 0, 0, 1, 1, out[0].data_ptr(), _DT[dtype]),
+        L.check(engine.lib.fvhd_preprocess_tiles(engine.handle, stream, t.data_ptr(), 0, H, W, R, R, 0, 0, 1, 1, out[0].data_ptr(), _DT[dtype]),
                 engine.handle)
-        L.check(engine.lib.fvhd_preprocess_tiles(engine.handle, stream, t.data_ptr(), on_host, H, W, nh, nw, py, px, ty, tx, out[1:].data_ptr(), _DT[dtype]),
+        L.check(engine.lib.fvhd_preprocess_tiles(engine.handle, stream, t.data_ptr(), 0, H, W, nh, nw, py, px, ty, tx, out[1:].data_ptr(), _DT[dtype]),
                 engine.handle)
-        if on_host:
-            torch.cuda.current_stream(dev).synchronize()              # the pinned staging tensor must outlive the async copies
+        t.record_stream(torch.cuda.current_stream(dev))               # the staging tensor is read asynchronously
     return out
 
 
