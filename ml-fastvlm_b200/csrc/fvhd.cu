@@ -1178,10 +1178,18 @@ static int preprocess_impl(fvhd_handle h, cudaStream_t st, const void* rgb, int 
     if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "preprocess horizontal pass: %s", cudaGetErrorString(e));
     // vertical pass (identity table when oh == Hs: one tap of weight 1 << 22 -> exact copy)
     if ((rc = rs_get_table(h, Hs, oh, &ty)) != FVHD_OK) return rc;
-    const dim3 g2((R + 127) / 128, R, tiles_y * tiles_x);
-    if (out_dtype == FVHD_F32) e = launch_k(resample_v_crop_kernel<float>, g2, dim3(128), 0, st, (const uint8_t*)h->rs_tmp, ow, oh, (float*)out, R, top, left, tiles_x, (const int*)ty.bounds, (const int*)ty.kk, ty.ksize, (const float*)h->rs_lut);
-    else if (out_dtype == FVHD_F16) e = launch_k(resample_v_crop_kernel<__half>, g2, dim3(128), 0, st, (const uint8_t*)h->rs_tmp, ow, oh, (__half*)out, R, top, left, tiles_x, (const int*)ty.bounds, (const int*)ty.kk, ty.ksize, (const float*)h->rs_lut);
-    else e = launch_k(resample_v_crop_kernel<bf16>, g2, dim3(128), 0, st, (const uint8_t*)h->rs_tmp, ow, oh, (bf16*)out, R, top, left, tiles_x, (const int*)ty.bounds, (const int*)ty.kk, ty.ksize, (const float*)h->rs_lut);
+    const int* yb = (const int*)ty.bounds; const int* yk = (const int*)ty.kk; const float* lut = (const float*)h->rs_lut; const uint8_t* tmp = (const uint8_t*)h->rs_tmp;
+    if (tiles_y * tiles_x == 1 && top >= 0 && left >= 0 && top + R <= oh && left + R <= ow) {       // one window inside the image
+        const dim3 g2((R + 127) / 128, R);
+        if (out_dtype == FVHD_F32) e = launch_k(resample_v_crop_kernel<float>, g2, dim3(128), 0, st, tmp, ow, (float*)out, R, top, left, yb, yk, ty.ksize, lut);
+        else if (out_dtype == FVHD_F16) e = launch_k(resample_v_crop_kernel<__half>, g2, dim3(128), 0, st, tmp, ow, (__half*)out, R, top, left, yb, yk, ty.ksize, lut);
+        else e = launch_k(resample_v_crop_kernel<bf16>, g2, dim3(128), 0, st, tmp, ow, (bf16*)out, R, top, left, yb, yk, ty.ksize, lut);
+    } else {                                                                                         // tiles of a canvas: black outside the image
+        const dim3 g2((R + 127) / 128, R, tiles_y * tiles_x);
+        if (out_dtype == FVHD_F32) e = launch_k(resample_v_tiles_kernel<float>, g2, dim3(128), 0, st, tmp, ow, oh, (float*)out, R, top, left, tiles_x, yb, yk, ty.ksize, lut);
+        else if (out_dtype == FVHD_F16) e = launch_k(resample_v_tiles_kernel<__half>, g2, dim3(128), 0, st, tmp, ow, oh, (__half*)out, R, top, left, tiles_x, yb, yk, ty.ksize, lut);
+        else e = launch_k(resample_v_tiles_kernel<bf16>, g2, dim3(128), 0, st, tmp, ow, oh, (bf16*)out, R, top, left, tiles_x, yb, yk, ty.ksize, lut);
+    }
     if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "preprocess vertical pass: %s", cudaGetErrorString(e));
     return FVHD_OK;
 }

@@ -103,14 +103,41 @@ template <> __device__ __forceinline__ float rs_cast<float>(float v) { return v;
 template <> __device__ __forceinline__ __half rs_cast<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ bf16 rs_cast<bf16>(float v) { return __float2bfloat16_rn(v); }
 
-// Vertical pass + window + x 1/255 (256-entry LUT, computed in double on the host) + NCHW store.
+// Vertical pass + centre crop + x 1/255 (256-entry LUT, computed in double on the host) + NCHW store: the window lies inside
+// the resized image.  tmp [Hs, ow, 3] u8 -> out [3, R, R] of T.  grid (ceil(R/128), R), 128 threads.
+template <typename T>
+__global__ void __launch_bounds__(128)
+resample_v_crop_kernel(const uint8_t* __restrict__ tmp, int ow, T* __restrict__ out, int R, int top, int left,
+                       const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, const float* __restrict__ lut) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int xo = blockIdx.x * 128 + threadIdx.x;
+    const int yo = blockIdx.y;
+    if (xo >= R) return;
+    const int yy = yo + top, xx = xo + left;
+    const int ymin = bounds[2 * yy], cnt = bounds[2 * yy + 1];
+    const int* kp = kk + (size_t)yy * ksize;
+    int a0 = 1 << (RS_PRECISION_BITS - 1), a1 = a0, a2 = a0;
+    for (int k = 0; k < cnt; ++k) {
+        const uint8_t* p = tmp + ((size_t)(ymin + k) * ow + xx) * 3;
+        const int c = kp[k];
+        a0 += p[0] * c; a1 += p[1] * c; a2 += p[2] * c;
+    }
+    const size_t plane = (size_t)R * R;
+    const size_t o = (size_t)yo * R + xo;
+    out[o] = rs_cast<T>(__ldg(lut + rs_clip8(a0)));
+    out[plane + o] = rs_cast<T>(__ldg(lut + rs_clip8(a1)));
+    out[2 * plane + o] = rs_cast<T>(__ldg(lut + rs_clip8(a2)));
+}
+
+// Tiled variant: vertical pass + window + x 1/255 (256-entry LUT, computed in double on the host) + NCHW store.
 // tmp [Hs, ow, 3] u8 (rows of the horizontally resized image) -> out [tiles, 3, R, R] of T.  Tile t = (ty, tx) = (t / tiles_x,
 // t % tiles_x) shows rows [top + ty R, +R) x cols [left + tx R, +R) of the vertically resized image (oh x ow); pixels outside
 // it are 0 (the black canvas of 'pad' / 'anyres').  The plain centre crop is one tile with top, left >= 0 inside the image.
 // grid (ceil(R/128), R, tiles), 128 threads.
 template <typename T>
 __global__ void __launch_bounds__(128)
-resample_v_crop_kernel(const uint8_t* __restrict__ tmp, int ow, int oh, T* __restrict__ out, int R, int top, int left, int tiles_x,
+resample_v_tiles_kernel(const uint8_t* __restrict__ tmp, int ow, int oh, T* __restrict__ out, int R, int top, int left, int tiles_x,
                        const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, const float* __restrict__ lut) {
     pdl_launch_dependents();
     pdl_wait();
