@@ -71,21 +71,27 @@ def get_anyres_image_grid_shape(image_size, grid_pinpoints, patch_size):
     return w // patch_size, h // patch_size
 
 
+def anyres_geometry(width, height, patch_size, grid_pinpoints):
+    """Host arithmetic of resize_and_pad_image + divide_to_patches (mm_utils.py:46-98) for an image of width x height:
+    -> (new_h, new_w, pad_y, pad_x, tiles_y, tiles_x): PIL-resize target, paste offset on the best-fit canvas, tile grid."""
+    pins = grid_pinpoints if isinstance(grid_pinpoints, list) else ast.literal_eval(grid_pinpoints)
+    cw, ch = select_best_resolution((width, height), [tuple(p) for p in pins])
+    sw, sh = cw / width, ch / height                                   # resize_and_pad_image, mm_utils.py:58-68
+    if sw < sh:
+        nw, nh = cw, min(math.ceil(height * sw), ch)
+    else:
+        nh, nw = ch, min(math.ceil(width * sh), cw)
+    R = patch_size                                                     # divide_to_patches: crops past the canvas are black too
+    return nh, nw, (ch - nh) // 2, (cw - nw) // 2, (ch + R - 1) // R, (cw + R - 1) // R
+
+
 def process_anyres_image(image, engine, grid_pinpoints, dtype=torch.float16):
     """mm_utils.py:121-147 on the GPU: [global view resized to R x R] + the R x R tiles of the image resized (aspect kept) and
     centred on the black best-fit canvas -> CUDA tensor [1 + tiles, 3, R, R].  Two library calls, bit-exact with the PIL path."""
-    pins = grid_pinpoints if isinstance(grid_pinpoints, list) else ast.literal_eval(grid_pinpoints)
     t = _as_u8_hwc(image)
     H, W = int(t.shape[0]), int(t.shape[1])
     R = engine.image_size
-    cw, ch = select_best_resolution((W, H), [tuple(p) for p in pins])
-    sw, sh = cw / W, ch / H                                            # resize_and_pad_image, mm_utils.py:58-68
-    if sw < sh:
-        nw, nh = cw, min(math.ceil(H * sw), ch)
-    else:
-        nh, nw = ch, min(math.ceil(W * sh), cw)
-    px, py = (cw - nw) // 2, (ch - nh) // 2
-    ty, tx = (ch + R - 1) // R, (cw + R - 1) // R                      # divide_to_patches: crops past the canvas are black too
+    nh, nw, py, px, ty, tx = anyres_geometry(W, H, R, grid_pinpoints)
     dev = engine.device
     out = torch.empty(1 + ty * tx, 3, R, R, dtype=dtype, device=dev)
     with torch.cuda.device(dev):

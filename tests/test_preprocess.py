@@ -114,6 +114,20 @@ def test_anyres_oracle_matches_reference_golden():
         assert pkg.select_best_resolution((w, h), pins) == po.select_best_resolution((w, h), pins)
 
 
+def test_anyres_host_geometry_matches_oracle_on_random_sizes():
+    """The host arithmetic that parameterises fvhd_preprocess_tiles (resize target, paste offset, tile grid) against the oracle's
+    restatement of resize_and_pad_image / divide_to_patches, over random image sizes and pin sets (incl. non-multiples of R)."""
+    rng = np.random.default_rng(7)
+    for _ in range(500):
+        R = int(rng.choice([64, 128, 336, 1024]))
+        w, h = int(rng.integers(8, 4000)), int(rng.integers(8, 4000))
+        pins = [(int(R * a), int(R * b)) for a, b in rng.choice([1, 2, 3, 1.5], size=(int(rng.integers(1, 6)), 2))]
+        cw, ch, nw, nh, px, py = po.anyres_geometry(w, h, pins)
+        got = pkg.anyres_geometry(w, h, R, pins)
+        assert got == (nh, nw, py, px, -(-ch // R), -(-cw // R)), (w, h, R, pins)
+        assert 1 <= nh <= ch and 1 <= nw <= cw and py >= 0 and px >= 0
+
+
 @pytest.mark.gpu
 def test_gpu_anyres_bit_exact():
     dev = torch.device("cuda:0")
