@@ -14,7 +14,7 @@ no collective on the data path (weak scaling).
              L2 flushed (256 MiB write) between timed steps.
   e2e        same metric through the host-buffer C-ABI entry (fvhd_encode_images_host): pinned fp16 host
              images -> H2D -> forward -> D2H of the projected tokens, all inside the timed region.
-  roofline   dominant kernel (tcgen05 GEMM): algorithmic FLOPs of all its launches in one step / their
+  roofline   dominant kernels (tcgen05 GEMM + the two fused ConvFFN kernels): algorithmic FLOPs of all their launches in one step / their
              summed live CUDA-event durations, against the measured bf16 peak (MEASURED_PEAKS.json).
   cpu_baseline  oracle port (fp32 torch CPU restatement of the reference) timed on the host cores, N=1 only.
 """
