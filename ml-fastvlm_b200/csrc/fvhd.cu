@@ -907,28 +907,31 @@ int fvhd_unit_info(fvhd_handle h, int u, const char** name, int64_t* in_elems, i
 }
 
 int fvhd_launches_per_forward(fvhd_handle h, int batch) {
-    if (!h) return FVHD_ERR_INVALID;
-    // steps per pass, + 2 for the three-kernel SE step, x number of passes
-    const int batch_per_pass = batch < h->cfg.max_batch ? batch : h->cfg.max_batch;
-    int steps = 0;
-    for (const UnitDesc& u : h->units) {
-        switch (u.kind) {
-        case 0: steps += 2; break;
-        case 1: {
-            const int tiles_m = (batch_per_pass * u.hout * u.wout + GEMM_BM - 1) / GEMM_BM;
-            steps += ((g_use_fused_mlp && u.cin <= 192) ||
-                      (g_use_cluster_mlp && u.cin == MLPC_C && h->mlpc_clusters > 0 && tiles_m <= 2 * h->mlpc_clusters)) ? 2 : 3;
-            break;
+    if (!h || batch < 1) return FVHD_ERR_INVALID;
+    // kernels of one pass over `bc` images (the plan build_plan makes for that batch size), + set_io_kernel
+    auto pass_launches = [&](int bc) {
+        int steps = 0;
+        for (const UnitDesc& u : h->units) {
+            switch (u.kind) {
+            case 0: steps += 2; break;
+            case 1: {
+                const int tiles_m = (bc * u.hout * u.wout + GEMM_BM - 1) / GEMM_BM;
+                steps += ((g_use_fused_mlp && u.cin <= 192) ||
+                          (g_use_cluster_mlp && u.cin == MLPC_C && h->mlpc_clusters > 0 && tiles_m <= 2 * h->mlpc_clusters)) ? 2 : 3;
+                break;
+            }
+            case 2: steps += 2; break;
+            case 3: steps += 1; break;
+            case 4: steps += 7; break;
+            case 5: steps += 4; break;   // dw + pool + reduce + expand
+            case 6: steps += h->cfg.projector_depth; break;
+            }
         }
-        case 2: steps += 2; break;
-        case 3: steps += 1; break;
-        case 4: steps += 7; break;
-        case 5: steps += 4; break;   // dw + pool + reduce + expand
-        case 6: steps += h->cfg.projector_depth; break;
-        }
-    }
-    const int passes = (batch + h->cfg.max_batch - 1) / h->cfg.max_batch;
-    return (steps + 1 /*set_io_kernel*/) * passes;
+        return steps + 1;
+    };
+    // fvhd_forward walks the batch in passes of max_batch images, the last one possibly smaller
+    const int full = batch / h->cfg.max_batch, rem = batch % h->cfg.max_batch;
+    return full * pass_launches(h->cfg.max_batch) + (rem ? pass_launches(rem) : 0);
 }
 
 int fvhd_forward(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch, void* tokens, void* projected) {
