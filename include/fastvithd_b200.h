@@ -95,6 +95,15 @@ int fvhd_forward(fvhd_handle h, void* stream, const void* images, int img_dtype,
 int fvhd_forward_strided(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch,
                          void* tokens, void* projected, long long out_image_stride);
 
+/* Batch-sharded encode_images whose projector epilogue IS the all-gather (the exchange step that
+ * follows mobileclip_encoder.py:84-86 + llava_arch.py:141-144 when one LLM prefill consumes the whole batch):
+ * this rank encodes its `batch` images and every 16-byte output vector is stored (a) at local_out and (b) at the same
+ * element offset of each peer_out[i] -- peer-mapped device pointers (CUDA IPC / symmetric memory, NVLink P2P) to the
+ * slot `[first_image_of_this_rank, +batch)` of GPU i's gathered [B_total, N, H] buffer.  No collective pass follows;
+ * the caller only has to order readers after all ranks' kernels (a barrier).  n_peers <= 8; requires a projector. */
+int fvhd_forward_gather(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch,
+                        void* local_out, void* const* peer_out, int n_peers);
+
 /* Same call with HOST buffers: H2D of the images, the forward, D2H of the result, one stream sync.
  * `host_out` receives `projected` when the plan has a projector, else `tokens` (bf16). */
 int fvhd_encode_images_host(fvhd_handle h, void* stream, const void* host_images, int img_dtype, int batch,

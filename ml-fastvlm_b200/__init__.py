@@ -21,6 +21,6 @@ from .glue import encode_images, splice_visual_tokens, EncodeImagesMixin, patch_
 from .checkpoint import read_state_dicts, load_pretrained  # noqa: F401
 from .preprocess import (process_images, preprocess_into, resample_coeffs, process_anyres_image, select_best_resolution,  # noqa: F401
                          get_anyres_image_grid_shape, anyres_geometry)
-from .parallel import shard_bounds, shard_batch, all_gather_tokens, encode_images_sharded  # noqa: F401
+from .parallel import shard_bounds, shard_batch, all_gather_tokens, encode_images_sharded, gather_slots, GatheredEncoder  # noqa: F401
 
 __version__ = "0.1.0"

@@ -747,8 +747,11 @@ int run_steps(fvhd_handle h, Plan& pl, int s0, int s1, cudaStream_t st, const Ru
     return FVHD_OK;
 }
 
-int set_io(fvhd_handle h, Plan& pl, cudaStream_t st, const void* images, void* final_out, void* tokens_out, long long final_image_stride) {
-    cudaError_t e = launch_k(set_io_kernel, dim3(1), dim3(1), 0, st, pl.io, images, final_out, tokens_out, final_image_stride);
+int set_io(fvhd_handle h, Plan& pl, cudaStream_t st, const void* images, void* final_out, void* tokens_out, long long final_image_stride,
+           const PeerList* peers = nullptr) {
+    PeerList pl_peers{};
+    if (peers) pl_peers = *peers;
+    cudaError_t e = launch_k(set_io_kernel, dim3(1), dim3(1), 0, st, pl.io, images, final_out, tokens_out, final_image_stride, pl_peers);
     if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "set_io_kernel launch failed: %s", cudaGetErrorString(e));
     return FVHD_OK;
 }
@@ -934,12 +937,41 @@ int fvhd_launches_per_forward(fvhd_handle h, int batch) {
     return full * pass_launches(h->cfg.max_batch) + (rem ? pass_launches(rem) : 0);
 }
 
+}  // extern "C"
+
+namespace {
+int forward_impl(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch, void* tokens, void* projected,
+                 long long out_image_stride, void* const* peer_out, int n_peers);
+}
+
+extern "C" {
+
 int fvhd_forward(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch, void* tokens, void* projected) {
-    return fvhd_forward_strided(h, stream, images, img_dtype, batch, tokens, projected, 0);
+    return forward_impl(h, stream, images, img_dtype, batch, tokens, projected, 0, nullptr, 0);
 }
 
 int fvhd_forward_strided(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch, void* tokens, void* projected,
                          long long out_image_stride) {
+    return forward_impl(h, stream, images, img_dtype, batch, tokens, projected, out_image_stride, nullptr, 0);
+}
+
+int fvhd_forward_gather(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch, void* local_out,
+                        void* const* peer_out, int n_peers) {
+    if (!h) return FVHD_ERR_INVALID;
+    if (h->cfg.projector_hidden <= 0) return fail(h, FVHD_ERR_INVALID, "fvhd_forward_gather needs a plan with a projector (the gathered tensor is the projected tokens)");
+    if (n_peers < 0 || n_peers > FVHD_MAX_PEERS) return fail(h, FVHD_ERR_INVALID, "n_peers %d outside [0, %d]", n_peers, FVHD_MAX_PEERS);
+    if (n_peers > 0 && !peer_out) return fail(h, FVHD_ERR_INVALID, "peer_out is null");
+    for (int i = 0; i < n_peers; ++i)
+        if (!peer_out[i] || ((uintptr_t)peer_out[i] & 15)) return fail(h, FVHD_ERR_INVALID, "peer_out[%d] must be a non-null, 16-B aligned device pointer", i);
+    if (!local_out) return fail(h, FVHD_ERR_INVALID, "local_out is null");
+    return forward_impl(h, stream, images, img_dtype, batch, nullptr, local_out, 0, peer_out, n_peers);
+}
+
+}  // extern "C"
+
+namespace {
+int forward_impl(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch, void* tokens, void* projected,
+                 long long out_image_stride, void* const* peer_out, int n_peers) {
     int rc = check_ready(h, batch);
     if (rc != FVHD_OK) return rc;
     if (!images) return fail(h, FVHD_ERR_INVALID, "images is null");
@@ -971,7 +1003,10 @@ int fvhd_forward_strided(fvhd_handle h, void* stream, const void* images, int im
         if (has_proj) {
             // tokens stay in the workspace (the projector's TMA map points there); copied out if requested
             const int last_unit = projected ? nunits - 1 : nunits - 2;
-            if ((rc = set_io(h, *pl, st, img, prj_dst, tok_dst, final_stride)) != FVHD_OK) return rc;
+            PeerList peers{};
+            peers.n = n_peers;
+            for (int i = 0; i < n_peers; ++i) peers.p[i] = reinterpret_cast<uint8_t*>(peer_out[i]) + (size_t)b0 * prj_stride;
+            if ((rc = set_io(h, *pl, st, img, prj_dst, tok_dst, final_stride, &peers)) != FVHD_OK) return rc;
             if ((rc = run_forward(h, *pl, st, ctx, pl->unit_steps[last_unit].second, tok_dst ? pl->unit_out[tok_unit] : nullptr,
                                   (size_t)bc * tok_stride)) != FVHD_OK) return rc;
         } else {
@@ -981,13 +1016,15 @@ int fvhd_forward_strided(fvhd_handle h, void* stream, const void* images, int im
     }
     return FVHD_OK;
 }
+}  // namespace
+
+extern "C" {
 
 int fvhd_encode_images_host(fvhd_handle h, void* stream, const void* host_images, int img_dtype, int batch, void* host_out) {
     int rc = check_ready(h, batch);
     if (rc != FVHD_OK) return rc;
     if (!host_images || !host_out) return fail(h, FVHD_ERR_INVALID, "null host buffer");
-    if (batch > h->cfg.max_batch) return fail(h, FVHD_ERR_INVALID, "fvhd_encode_images_host: batch %d > max_batch %d", batch, h->cfg.max_batch);
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);      // batches above max_batch run in passes inside fvhd_forward
     const size_t img_bytes = (size_t)batch * 3 * h->R * h->R * dtype_size(img_dtype);
     const size_t out_bytes = (size_t)batch * h->ntok * fvhd_out_dim(h) * 2;
     // device staging owned by the handle (grown on demand)

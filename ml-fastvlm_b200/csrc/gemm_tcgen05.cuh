@@ -146,6 +146,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (lane == 0) {
             // ---------------- TMA producer
             const uint32_t a_slice = GEMM_A_STAGE_BYTES / (uint32_t)CS, b_slice = b_stage_bytes / (uint32_t)CS;
+            // W (the B operand) is a constant of the forward: the first ring fill of weight boxes is issued BEFORE the PDL wait,
+            // so it overlaps the predecessor's tail; only the A boxes (the predecessor's output) wait for it.
+            int pre = 0;
+            if (CS == 1) {
+                for (int ct = cid; ct < p.ctiles && pre < stages; ct += nclusters) {
+                    int m0, n0;
+                    tile_origin(ct, m0, n0);
+                    for (int kb = 0; kb < num_kb && pre < stages; ++kb, ++pre) {
+                        mbar_expect_tx(&full_bar[pre], GEMM_A_STAGE_BYTES + b_stage_bytes);
+                        tma_load_2d(smemB + (size_t)pre * b_stage_bytes, &tmB, kb * GEMM_BK, n0, &full_bar[pre]);
+                    }
+                }
+            }
             pdl_wait();                                     // A is the previous kernel's output
             GEMM_TRACE(2);
             int it = 0;
@@ -155,10 +168,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % stages;
                     const uint32_t ph = (uint32_t)(it / stages) & 1u;
-                    mbar_wait(&empty_bar[s], ph ^ 1u);       // slot s is free in EVERY CTA of the cluster
-                    mbar_expect_tx(&full_bar[s], GEMM_A_STAGE_BYTES + b_stage_bytes);
                     uint8_t* sa = smemA + (size_t)s * GEMM_A_STAGE_BYTES;
                     uint8_t* sb = smemB + (size_t)s * b_stage_bytes;
+                    if (it < pre) {                          // slot armed and its W box already in flight
+                        tma_load_2d(sa, &tmA, kb * GEMM_BK, m0, &full_bar[s]);
+                        continue;
+                    }
+                    mbar_wait(&empty_bar[s], ph ^ 1u);       // slot s is free in EVERY CTA of the cluster
+                    mbar_expect_tx(&full_bar[s], GEMM_A_STAGE_BYTES + b_stage_bytes);
                     if (CS == 1) {
                         tma_load_2d(sa, &tmA, kb * GEMM_BK, m0, &full_bar[s]);
                         tma_load_2d(sb, &tmB, kb * GEMM_BK, n0, &full_bar[s]);
@@ -227,11 +244,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < p.M;
             bf16* drow;
+            size_t doff = 0;        // element offset of this row in the caller's buffer (and in every peer's gathered buffer)
+            int npeers = 0;
             if (p.D) {
                 drow = p.D + (size_t)row * p.ldd;
             } else {        // caller memory: image b's tokens start at final_out + b * final_image_stride
                 const int bi = row / p.rows_per_image;
-                drow = reinterpret_cast<bf16*>(p.io->final_out) + (size_t)bi * (size_t)p.io->final_image_stride + (size_t)(row - bi * p.rows_per_image) * p.ldd;
+                doff = (size_t)bi * (size_t)p.io->final_image_stride + (size_t)(row - bi * p.rows_per_image) * p.ldd;
+                drow = reinterpret_cast<bf16*>(p.io->final_out) + doff;
+                npeers = p.io->n_peers;
             }
             const bf16* rrow = p.residual ? p.residual + (size_t)row * p.ldr : nullptr;
             // ---- everything that does not depend on the accumulator is fetched BEFORE waiting for it: the bias of this
@@ -312,6 +333,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             *reinterpret_cast<uint4*>(srow + ((((uint32_t)(c * 4 + g8)) ^ sw) << 4)) = o;
                         } else if (row_ok && col_ok) {
                             *reinterpret_cast<uint4*>(drow + col) = o;
+                            // fused all-gather: the same 16 bytes go to this rank's slot in every peer GPU's gathered buffer
+                            for (int q = 0; q < npeers; ++q)
+                                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.io->peer_out[q]) + doff + col) = o;
                         }
                     }
                 }

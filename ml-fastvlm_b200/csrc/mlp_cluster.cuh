@@ -121,7 +121,6 @@ mlp_cluster_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid
     if (warp == 0) {
         if (lane == 0) {
             // ---------------- TMA producer: z tile, then half-chunk W boxes in the MMA thread's consumption order
-            pdl_wait();
             int wit = 0;
             auto load_w = [&](bool is_w2, int j, int u) {
                 const int s = wit % MLPC_SLOTS;
@@ -138,6 +137,18 @@ mlp_cluster_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid
                     tma_load_2d(dst, &tmW2, hid0 + j * MLP_NH, u * MLPC_NHALF, &w_full[s]);
                 }
             };
+            // half-chunk q of a tile's weight stream, in consumption order: W1[0] x2, then (W1[j] x2, W2[j-1] x2) j = 1..NC-1, W2[NC-1] x2
+            auto load_seq = [&](int q) {
+                if (q < 2) { load_w(false, 0, q); return; }
+                if (q >= 4 * MLPC_NC - 2) { load_w(true, MLPC_NC - 1, q - (4 * MLPC_NC - 2)); return; }
+                const int g = (q - 2) >> 2, r = (q - 2) & 3;
+                if (r < 2) load_w(false, g + 1, r); else load_w(true, g, r - 2);
+            };
+            // weights are constants of the forward: the first ring fill precedes the PDL wait (only z depends on the predecessor)
+            int q0 = 0;
+            if (cluster_id < p.tiles_m)
+                for (; q0 < MLPC_SLOTS; ++q0) load_seq(q0);
+            pdl_wait();
             int ti = 0;
             for (int tile = cluster_id; tile < p.tiles_m; tile += num_clusters, ++ti) {
                 mbar_wait(tile_done, ((uint32_t)ti & 1u) ^ 1u);                   // previous tile's receive buffer (z overlay) consumed ...
@@ -145,12 +156,7 @@ mlp_cluster_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid
                 MLPC_TRACE(2);
                 mbar_expect_tx(z_full, MLPC_Z_BYTES);
                 for (int kb = 0; kb < MLPC_KB; ++kb) tma_load_2d(smemZ + (size_t)kb * GEMM_A_STAGE_BYTES, &tmZ, kb * 64, tile * GEMM_BM, z_full);
-                load_w(false, 0, 0); load_w(false, 0, 1);
-                for (int j = 1; j < MLPC_NC; ++j) {
-                    load_w(false, j, 0); load_w(false, j, 1);
-                    load_w(true, j - 1, 0); load_w(true, j - 1, 1);
-                }
-                load_w(true, MLPC_NC - 1, 0); load_w(true, MLPC_NC - 1, 1);
+                for (int q = ti == 0 ? q0 : 0; q < 4 * MLPC_NC; ++q) load_seq(q);
             }
         }
     } else if (warp == 1) {

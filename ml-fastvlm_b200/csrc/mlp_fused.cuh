@@ -99,7 +99,6 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_c
     if (warp == 0) {
         if (lane == 0) {
             // ---------------- TMA producer: z tile, then the W1/W2 chunk boxes in the MMA thread's consumption order
-            pdl_wait();
             int wit = 0;
             auto load_w = [&](bool is_w2, int j) {
                 const int s = wit % MLP_SLOTS;
@@ -115,14 +114,25 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_c
                     tma_load_2d(dst, &tmW2, j * MLP_NH, 0, &w_full[s]);
                 }
             };
+            // the weight stream of one tile, in the MMA thread's consumption order: W1[0], (W1[j], W2[j-1]) j = 1..NC-1, W2[NC-1]
+            auto load_seq = [&](int q) {
+                if (q == 0) load_w(false, 0);
+                else if (q == 2 * NC - 1) load_w(true, NC - 1);
+                else if (q & 1) load_w(false, (q + 1) >> 1);
+                else load_w(true, (q >> 1) - 1);
+            };
+            // weights are constants of the forward: the first ring fill is issued BEFORE the PDL wait and overlaps the
+            // predecessor's tail; only z (the predecessor's output) has to wait
+            int q0 = 0;
+            if ((int)blockIdx.x < p.tiles_m)
+                for (; q0 < MLP_SLOTS && q0 < 2 * NC; ++q0) load_seq(q0);
+            pdl_wait();
             int ti = 0;
             for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x, ++ti) {
                 mbar_wait(z_empty, ((uint32_t)ti & 1u) ^ 1u);
                 mbar_expect_tx(z_full, (uint32_t)KB * GEMM_A_STAGE_BYTES);
                 for (int kb = 0; kb < KB; ++kb) tma_load_2d(smemZ + (size_t)kb * GEMM_A_STAGE_BYTES, &tmZ, kb * 64, tile * GEMM_BM, z_full);
-                load_w(false, 0);
-                for (int j = 1; j < NC; ++j) { load_w(false, j); load_w(true, j - 1); }
-                load_w(true, NC - 1);
+                for (int q = ti == 0 ? q0 : 0; q < 2 * NC; ++q) load_seq(q);
             }
         }
     } else if (warp == 1) {

@@ -13,6 +13,8 @@ namespace fvhd {
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;
 
+constexpr int FVHD_MAX_PEERS = 8;
+
 // Caller-owned pointers of one forward call, kept in device memory so that the launch sequence itself is
 // static (replayable as a CUDA graph): written by set_io_kernel, read by the first and last kernels.
 struct IoBlock {
@@ -21,6 +23,11 @@ struct IoBlock {
     void* tokens_out;       // optional copy-out of the tower tokens when a projector follows
     long long final_image_stride;   // elements between consecutive images in final_out (N*H when dense; L*H when the
                                     // destination is a [B, L, H] LLM embedding buffer -- the token splice, llava_arch.py:251-271)
+    // Fused all-gather: the projector epilogue ALSO stores every output vector at the same element offset in
+    // `n_peers` other GPUs' gathered buffers (peer-mapped device pointers: NVLink P2P stores issued by the kernel that
+    // runs the tcgen05 tiles), so no separate collective pass follows the projector.
+    int n_peers;
+    void* peer_out[FVHD_MAX_PEERS];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -77,6 +77,8 @@ class Engine:
         device = torch.device(device)
         if device.type != "cuda":
             raise L.FvhdError(f"libfastvithd_b200 computes on CUDA devices only (got {device}); there is no CPU path")
+        if device.index is None:                       # 'cuda' -> the concrete current device, so tensor.device compares equal
+            device = torch.device("cuda", torch.cuda.current_device())
         specs = self.weight_specs()
         offs, total = {}, 0
         for name, dt, numel in specs:
@@ -114,17 +116,28 @@ class Engine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ------------------------------------------------------------------ compute
+    def _check_images(self, images, device):
+        """Shape / dtype / placement of an image batch before its raw pointer goes to the C library; returns it contiguous."""
+        if self.device is None:
+            raise L.FvhdError("Engine.load() has not been called")
+        if not torch.is_tensor(images) or images.dim() != 4 or images.shape[0] < 1 or images.shape[1] != 3 \
+                or images.shape[2] != self.image_size or images.shape[3] != self.image_size:
+            raise L.FvhdError(f"images must be [B>=1,3,{self.image_size},{self.image_size}], got {tuple(getattr(images, 'shape', ()))}")
+        _img_dtype(images)
+        if images.device != device:
+            raise L.FvhdError(f"images on {images.device}, expected {device}")
+        return images.contiguous()
+
+    def _check_out(self, t, shape, what):
+        if not torch.is_tensor(t) or t.dtype != torch.bfloat16 or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+            raise L.FvhdError(f"{what} must be a contiguous bf16 tensor of shape {tuple(shape)}, got "
+                              f"{getattr(t, 'dtype', None)} {tuple(getattr(t, 'shape', ()))}")
+
     def forward(self, images, want_tokens=True, want_projected=None):
         """images: CUDA tensor [B,3,R,R] (fp32/fp16/bf16) -> (tokens [B,N,3072] bf16 | None, projected [B,N,H] bf16 | None)."""
         if want_projected is None:
             want_projected = self.hidden > 0
-        if self.device is None:
-            raise L.FvhdError("Engine.load() has not been called")
-        if images.dim() != 4 or images.shape[1] != 3 or images.shape[2] != self.image_size or images.shape[3] != self.image_size:
-            raise L.FvhdError(f"images must be [B,3,{self.image_size},{self.image_size}], got {tuple(images.shape)}")
-        if images.device != self.device:
-            raise L.FvhdError(f"images on {images.device}, engine on {self.device}")
-        images = images.contiguous()
+        images = self._check_images(images, self.device)
         B = images.shape[0]
         with torch.cuda.device(self.device):
             tokens = torch.empty(B, self.num_tokens, 3072, dtype=torch.bfloat16, device=self.device) if want_tokens else None
@@ -141,10 +154,12 @@ class Engine:
             raise L.FvhdError("forward_into needs a plan with a projector")
         if embeds.dtype != torch.bfloat16 or not embeds.is_contiguous() or embeds.dim() != 3 or embeds.shape[2] != self.hidden:
             raise L.FvhdError(f"embeds must be contiguous bf16 [B, L, {self.hidden}], got {embeds.dtype} {tuple(embeds.shape)}")
+        images = self._check_images(images, self.device)
+        if embeds.device != self.device:
+            raise L.FvhdError(f"embeds on {embeds.device}, engine on {self.device}")
         B, Lseq = embeds.shape[0], embeds.shape[1]
         if images.shape[0] != B or position < 0 or position + self.num_tokens > Lseq:
             raise L.FvhdError(f"cannot place {self.num_tokens} tokens at {position} in a sequence of {Lseq} (batch {images.shape[0]} vs {B})")
-        images = images.contiguous()
         with torch.cuda.device(self.device):
             dst = embeds.data_ptr() + position * self.hidden * 2
             L.check(self.lib.fvhd_forward_strided(self.handle, self._stream(), images.data_ptr(), _img_dtype(images), B, None, dst,
@@ -153,13 +168,36 @@ class Engine:
 
     def encode_images_host(self, host_images, host_out=None):
         """HOST tensors in, HOST tensor out (bf16): the e2e entry (H2D + forward + D2H inside the call)."""
+        host_images = self._check_images(host_images, torch.device("cpu"))
         B = host_images.shape[0]
         if host_out is None:
             host_out = torch.empty(B, self.num_tokens, self.out_dim, dtype=torch.bfloat16, pin_memory=True)
+        if host_out.device.type != "cpu":
+            raise L.FvhdError(f"host_out must be a CPU tensor, got {host_out.device}")
+        self._check_out(host_out, (B, self.num_tokens, self.out_dim), "host_out")
         with torch.cuda.device(self.device):
             L.check(self.lib.fvhd_encode_images_host(self.handle, self._stream(), host_images.data_ptr(), _img_dtype(host_images), B,
                                                      host_out.data_ptr()), self.handle)
         return host_out
+
+    def forward_gather(self, images, local_out, peer_ptrs):
+        """encode_images of this rank's shard with the all-gather fused into the projector's store: the projected tokens
+        are written to `local_out` ([b,N,H] bf16 view of this rank's slot in its own gathered buffer) AND, by the same
+        kernel, to `peer_ptrs` (ints: peer-mapped device addresses of this rank's slot in every other GPU's gathered
+        buffer).  The caller orders the readers (e.g. a symmetric-memory barrier) -- see parallel.GatheredEncoder."""
+        if self.hidden <= 0:
+            raise L.FvhdError("forward_gather needs a plan with a projector")
+        images = self._check_images(images, self.device)
+        B = images.shape[0]
+        if local_out.device != self.device:
+            raise L.FvhdError(f"local_out on {local_out.device}, engine on {self.device}")
+        self._check_out(local_out, (B, self.num_tokens, self.hidden), "local_out")
+        n = len(peer_ptrs)
+        arr = (C.c_void_p * max(n, 1))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        with torch.cuda.device(self.device):
+            L.check(self.lib.fvhd_forward_gather(self.handle, self._stream(), images.data_ptr(), _img_dtype(images), B,
+                                                 local_out.data_ptr(), arr, n), self.handle)
+        return local_out
 
     def run_units(self, first, last, x, batch):
         """Run units [first,last]; x = NCHW images (first == 0) or bf16 NHWC activation.  Returns bf16 [B, out_elems]."""

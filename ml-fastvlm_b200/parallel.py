@@ -49,13 +49,61 @@ def all_gather_tokens(local_tokens, batch, group=None):
 
 
 def encode_images_sharded(encode_fn, images, gather=True, group=None):
-    """Run `encode_fn` (e.g. `lambda x: engine.forward(x)[1]`) on this rank's shard; optionally all-gather."""
+    """Run `encode_fn` (e.g. `lambda x: engine.forward(x)[1]`) on this rank's shard; optionally all-gather (NCCL pass)."""
     batch = images.shape[0]
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    # decided identically on EVERY rank before any collective: a rank-local raise would leave the others inside the
+    # all-gather forever
+    if gather and batch < world:
+        raise ValueError(f"all-gather needs at least one image per rank (batch {batch} < world {world})")
     a, b = shard_bounds(batch, rank, world)
     local = encode_fn(images[a:b]) if b > a else None
     if not gather:
         return local
-    if local is None:
-        raise ValueError("all-gather needs at least one image per rank")
     return all_gather_tokens(local, batch, group)
+
+
+def gather_slots(batch, world):
+    """[(first_image, n_images)] of every rank's slot in the gathered [batch, N, H] buffer."""
+    return [(a, b - a) for a, b in (shard_bounds(batch, r, world) for r in range(world))]
+
+
+class GatheredEncoder:
+    """Batch-sharded encode_images whose projector epilogue IS the all-gather.
+
+    Every rank owns a symmetric-memory buffer [batch, N, H] (torch.distributed._symmetric_memory: CUDA-IPC / fabric handles
+    exchanged once at construction; NVLink peer mappings).  `encode(images_of_my_shard)` makes ONE library call
+    (`fvhd_forward_gather`): the projector GEMM's epilogue stores each output vector into this rank's slot of its own
+    buffer and, in the same kernel, into the same slot of every peer's buffer.  A symmetric-memory barrier then orders
+    all ranks' stores before any reader.  No NCCL collective is on the data path.
+    """
+
+    def __init__(self, engine, batch, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.engine = engine
+        self.batch = int(batch)
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.batch < self.world:
+            raise ValueError(f"gathered encode needs at least one image per rank (batch {self.batch} < world {self.world})")
+        if self.world - 1 > 8:
+            raise ValueError("at most 8 peers (one NVSwitch domain)")
+        n, h = engine.num_tokens, engine.hidden
+        self.buf = symm_mem.empty((self.batch, n, h), dtype=torch.bfloat16, device=engine.device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.slots = gather_slots(self.batch, self.world)
+        a, nb = self.slots[self.rank]
+        off = a * n * h * 2                      # byte offset of this rank's slot -- the same in every rank's buffer
+        self.local = self.buf[a:a + nb]
+        self.peer_ptrs = [int(self.hdl.buffer_ptrs[r]) + off for r in range(self.world) if r != self.rank]
+
+    def encode(self, my_images, barrier=True):
+        """my_images: this rank's [b_r,3,R,R] shard.  Returns the gathered [batch, N, H] tensor (valid after the barrier)."""
+        a, nb = self.slots[self.rank]
+        if my_images.shape[0] != nb:
+            raise ValueError(f"rank {self.rank}: expected {nb} local images, got {my_images.shape[0]}")
+        self.engine.forward_gather(my_images, self.local, self.peer_ptrs)
+        if barrier:
+            self.hdl.barrier(channel=0)          # stream-ordered: all ranks' peer stores precede the readers
+        return self.buf

@@ -2,7 +2,8 @@
 
 Module structure and state-dict keys are the reference's (`nn.Sequential` of Linear / GELU / Linear ->
 `0.weight, 0.bias, 2.weight, 2.bias`; bare `nn.Linear` for "linear"); `forward` runs the tcgen05 GEMM with
-the bias / exact-erf-GELU epilogue instead of ATen.
+the bias / GELU epilogue instead of ATen (GELU = erf form evaluated as 0.5x(1+tanh(x P(x^2))), |error| <= 3e-5,
+see csrc/ptx.cuh gelu_erf).
 """
 import re
 from collections import OrderedDict
@@ -12,15 +13,18 @@ import torch.nn as nn
 
 from .lib import FvhdError
 
-_util_engine = None
+_util_engines = {}
 
 
-def _gemm_engine():
-    global _util_engine
-    if _util_engine is None:
+def _gemm_engine(device):
+    """Plan-less handle for the stand-alone GEMM entry, one per CUDA device: the library's per-device setup
+    (max dynamic smem attribute, SM count) is done by whichever device is current at the first call of a handle."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    eng = _util_engines.get(key)
+    if eng is None:
         from .engine import Engine
-        _util_engine = Engine(64, 0, 2, 1)       # plan-less use: only the stand-alone GEMM entry
-    return _util_engine
+        eng = _util_engines[key] = Engine(64, 0, 2, 1)
+    return eng
 
 
 class _PackedMixin:
@@ -59,7 +63,7 @@ class _PackedMixin:
     def _run(self, x):
         if x.device.type != "cuda":
             raise FvhdError(f"mm_projector computes on CUDA (sm_100a) only; input is on {x.device}. No CPU fallback exists.")
-        eng = _gemm_engine()
+        eng = _gemm_engine(x.device)
         shape = x.shape
         a = x.reshape(-1, shape[-1]).to(torch.bfloat16).contiguous()
         ws = self._device_pack(x.device)
@@ -85,6 +89,9 @@ class FastVLMProjector(_PackedMixin, nn.Sequential):
         return [m for m in self if isinstance(m, nn.Linear)]
 
     def forward(self, x):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("libfastvithd_b200 is inference-only: training mm_projector needs the reference projector "
+                                      "(call under torch.no_grad() or freeze it)")
         with torch.no_grad():
             return self._run(x)
 
@@ -100,6 +107,9 @@ class FastVLMLinearProjector(_PackedMixin, nn.Linear):
         return [self]
 
     def forward(self, x):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("libfastvithd_b200 is inference-only: training mm_projector needs the reference projector "
+                                      "(call under torch.no_grad() or freeze it)")
         with torch.no_grad():
             return self._run(x)
 

@@ -148,25 +148,40 @@ class FastViTHDVisionTower(nn.Module):
         """The library already emits [B, HW, C]; kept for API parity (mobileclip_encoder.py:60-68)."""
         return image_forward_outs["image_embeddings"]
 
+    def _refuse_training(self, projector=None):
+        """The reference runs the tower under grad when `tune_vision_tower` is set (mobileclip_encoder.py:70-75).  This library has
+        no backward: fail loudly BEFORE entering no_grad instead of silently returning detached features."""
+        if not torch.is_grad_enabled():
+            return
+        if self.tune_vision_tower or any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("libfastvithd_b200 is inference-only: encoder backward (unfreeze_mm_vision_tower) is out of scope; "
+                                      "call under torch.no_grad() / freeze the tower")
+        if projector is not None and any(p.requires_grad for p in projector.parameters()):
+            raise NotImplementedError("libfastvithd_b200 is inference-only: mm_projector training needs the reference projector; "
+                                      "call under torch.no_grad() / freeze the projector")
+
     def forward(self, images):
+        self._refuse_training()
         with torch.no_grad():
             return self.forward_images(images)
 
     def forward_images(self, images):
         eng = self.engine()
         if type(images) is list:
-            image_features = []
-            for image in images:
-                x = image.to(device=self.device, dtype=self.dtype).unsqueeze(0)
-                tokens, _ = eng.forward(x, want_tokens=True, want_projected=False)
-                image_features.append(tokens.to(image.dtype))
-            return image_features
+            # the reference loops one image at a time (mobileclip_encoder.py:78-83); images are independent through the tower,
+            # so the list goes through ONE batched call and is split back into the reference's list of [1, N, C]
+            if len(images) == 0:
+                return []
+            x = torch.stack([image.to(device=self.device, dtype=self.dtype) for image in images], 0)
+            tokens, _ = eng.forward(x, want_tokens=True, want_projected=False)
+            return [tokens[i:i + 1].to(image.dtype) for i, image in enumerate(images)]
         x = images.to(device=self.device, dtype=self.dtype)
         tokens, _ = eng.forward(x, want_tokens=True, want_projected=False)
         return tokens.to(images.dtype)
 
     def encode_with_projector(self, images, projector):
         """mm_projector(tower(images)) as ONE call (llava_arch.py:141-144)."""
+        self._refuse_training(projector)
         with torch.no_grad():
             eng = self.fused_engine(projector)
             x = images.to(device=self.device, dtype=self.dtype)

@@ -2,7 +2,7 @@
 unmodified reference, and size-independent properties at the bench size.
 
 Tolerances (bf16 activations + bf16 GEMM weights, fp32 accumulation, vs the fp32 oracle):
-  * a single unit fed the oracle's own input ........ rel-L2 <= 1.5e-2
+  * a single unit fed the oracle's own input ........ rel-L2 <= 8e-3 (measured 2.3e-3 .. 4.5e-3)
   * whole tower / encode_images (51 units chained) .. rel-L2 <= 5e-2 AND <= 1.25 x the error of the
     reference algorithm's own bf16 run (PyTorch bf16, same fixture: 3.8e-2 at R=256; bf16 weight
     rounding alone gives ~7e-3; measured CUDA path: 3.3e-2)
@@ -20,7 +20,7 @@ from oracle import fixture as fx
 
 pytestmark = pytest.mark.gpu
 
-UNIT_TOL = 1.5e-2
+UNIT_TOL = 8e-3
 E2E_TOL = 5e-2
 
 
@@ -384,8 +384,11 @@ def test_tower_and_projector_modules(tower_sd, proj_sd, oracle256, golden_dir, d
         def get_vision_tower(self):
             return tower
     m = Model()
-    fused = pkg.encode_images(m, fx.synthetic_images(1, 256).to(dev))
-    split = proj(tower(fx.synthetic_images(1, 256).to(dev)))
+    with pytest.raises(NotImplementedError):            # nn.Linear parameters require grad by default: training is refused loudly
+        proj(feats.to(dev))
+    with torch.inference_mode():                        # predict.py:60 / HF generate run the path without grad
+        fused = pkg.encode_images(m, fx.synthetic_images(1, 256).to(dev))
+        split = proj(tower(fx.synthetic_images(1, 256).to(dev)))
     assert tuple(fused.shape) == (1, 16, 896)
     assert rel_l2(fused, ref) < E2E_TOL and rel_l2(split, ref) < E2E_TOL
     assert rel_l2(fused, split) < 5e-3                  # same kernels; split path rounds tokens through fp32->bf16 once more

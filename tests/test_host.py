@@ -122,7 +122,9 @@ def test_projector_drop_in_surface(proj_sd):
     proj = pkg.build_vision_projector(Cfg())
     assert list(proj.state_dict().keys()) == ["0.weight", "0.bias", "2.weight", "2.bias"]
     proj.load_state_dict(proj_sd, strict=True)
-    with pytest.raises(pkg.FvhdError):
+    with pytest.raises(NotImplementedError):     # parameters require grad by default: training is refused loudly (inference-only library)
+        proj(torch.rand(1, 16, 3072))
+    with torch.no_grad(), pytest.raises(pkg.FvhdError):     # no CPU fallback
         proj(torch.rand(1, 16, 3072))
     Cfg.mm_projector_type = "linear"
     assert list(pkg.build_vision_projector(Cfg()).state_dict().keys()) == ["weight", "bias"]
