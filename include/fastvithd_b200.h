@@ -167,6 +167,12 @@ int fvhd_debug_mixer_trace(void* dev_buf_8_u64_per_cta);
 int fvhd_gemm(fvhd_handle h, void* stream, const void* A, const void* W, const void* bias, const void* residual,
               void* D, int M, int N, int K, int act);
 
+/* Test entry: the RepMixer depthwise pair of one block on the tcgen05 mixer kernel (mixer_umma.cuh), mci.py:808-811 + :921:
+ *   y = dw3x3(x) + b3,  z = dw7x7(y) + b7;  x, y, z device bf16 NHWC [B,H,W,C]; w3 [9][C], w7 [49][C], b3, b7 [C] fp32 (tap-major,
+ *   BN folded).  C % 16 == 0. */
+int fvhd_mixer(fvhd_handle h, void* stream, const void* x, const void* w3, const void* b3, const void* w7, const void* b7,
+               void* y, void* z, int batch, int H, int W, int C);
+
 /* Stand-alone fused ConvFFN entry (tests, traces): out[M,C] = resid + fc2(GELU(fc1(z) + b1)) + b2  (mci.py:922-926 with the
  * layer scale folded into w2 / b2), bf16 operands, fp32 biases; w1 [4C, C], w2 [C, 4C] row-major.  C = 96 / 192 run the
  * single-CTA kernel, C = 384 the 4-CTA-cluster kernel (hidden split across the cluster, DSMEM reduction); `trace` (C = 384

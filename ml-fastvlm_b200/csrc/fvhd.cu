@@ -22,6 +22,7 @@
 #include "preprocess.cuh"
 #include "stem_attn_se.cuh"
 #include "mixer_tc.cuh"
+#include "mixer_umma.cuh"
 
 using namespace fvhd;
 
@@ -269,6 +270,7 @@ int g_gemm_max_cs = 1;        // FVHD_GEMM_CS=1|2|4 caps the GEMM cluster size. 
                               // the limit and multicast only reduces L2 reads -- measured no gain (profiles/r01_f_summary.md)
 bool g_use_cluster_mlp = true; // FVHD_NO_CLUSTER_MLP=1: stage-2 (C = 384) ConvFFN as two GEMM launches instead of the 4-CTA-cluster kernel
 bool g_use_fused_mlp = true;  // FVHD_NO_FUSED_MLP=1: ConvFFN as two GEMM launches (reference path of the bit-exactness test)
+char g_mixer_mode = 't';       // FVHD_MIXER=u: tcgen05 mixer (mixer_umma.cuh); t: mma.sync 7x7 (mixer_tc.cuh); f: FMA pipes (dwconv.cuh)
 unsigned long long* g_gemm_trace = nullptr;   // fvhd_debug_gemm_trace: device buffer, 16 stamps per CTA
 int g_force_bn = 0;                            // fvhd_debug_gemm_trace: force the N tile (0 = cost model)
 template <typename... KArgs, typename... Args>
@@ -344,6 +346,8 @@ int ensure_cuda(fvhd_handle h) {
     CUDA_TRY(h, set_smem(repmixer_dw_kernel<8, 16, 128>, MixCfgT<8, 16>::SMEM));
     CUDA_TRY(h, set_smem(repmixer_dw_kernel<16, 16, 512, 6, 4, 2>, MixCfgT<16, 16>::SMEM));
     CUDA_TRY(h, set_smem(repmixer_tc_kernel, MixTc::SMEM));
+    CUDA_TRY(h, set_smem(repmixer_umma_kernel, MixU::SMEM));
+    { const char* e = getenv("FVHD_MIXER"); if (e && e[0]) g_mixer_mode = e[0]; }
     CUDA_TRY(h, set_smem(dwconv_kernel<7, 1, 1, 0, 16, 16, 8>, DwCfg<7, 1, 1, 16, 16>::SMEM));
     CUDA_TRY(h, set_smem(dwconv_kernel<7, 2, 2, 1, 8, 8, 4>, DwCfg<7, 2, 2, 8, 8>::SMEM));
     CUDA_TRY(h, set_smem(dwconv_kernel<3, 1, 2, 0, 16, 16, 8>, DwCfg<3, 1, 2, 16, 16>::SMEM));
@@ -382,6 +386,46 @@ int make_tmap_nhwc(fvhd_handle h, CUtensorMap* m, const void* ptr, int B, int H,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, FVHD_ERR_CUDA, "cuTensorMapEncodeTiled(4D) failed (%d) B=%d H=%d W=%d C=%d box=%dx%d", (int)r, B, H, W, C, box_w, box_h);
+    return FVHD_OK;
+}
+
+// NHWC bf16 activation [B, H, W, C] viewed as {8 ch, W, H, C/8, B} -> 5-D tensor map, box {8, box_w, box_h, 2 chunks, 1}: lands in smem
+// as [8-channel chunk][row][x][8 ch] -- the no-swizzle K-major core-matrix layout of mixer_umma.cuh.  Zero OOB fill.
+int make_tmap_chunked(fvhd_handle h, CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int box_w, int box_h) {
+    if ((uintptr_t)ptr & 15) return fail(h, FVHD_ERR_INVALID, "TMA operand must be 16-B aligned (ptr %p)", ptr);
+    cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / 8), (cuuint64_t)B};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, 16, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[5] = {8, (cuuint32_t)box_w, (cuuint32_t)box_h, 2, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, FVHD_ERR_CUDA, "cuTensorMapEncodeTiled(5D) failed (%d) B=%d H=%d W=%d C=%d box=%dx%d", (int)r, B, H, W, C, box_w, box_h);
+    return FVHD_OK;
+}
+
+// RepMixer depthwise pair on tcgen05 (mixer_umma.cuh): persistent CTAs, two per SM, each bound to one 16-channel group.
+int make_mixer_umma_step(fvhd_handle h, Step* st, const bf16* x, bf16* y, bf16* z, const float* w3, const float* b3, const float* w7,
+                         const float* b7, int batch, int H, int W, int C) {
+    if (C % 16) return fail(h, FVHD_ERR_INVALID, "tcgen05 mixer needs C %% 16 == 0 (got %d)", C);
+    MixUParams mp{};
+    mp.y = y; mp.z = z; mp.w3 = w3; mp.b3 = b3; mp.w7 = w7; mp.b7 = b7;
+    mp.B = batch; mp.H = H; mp.W = W; mp.C = C;
+    mp.tiles_x = (W + MixU::TOW - 1) / MixU::TOW;
+    mp.tiles_y = (H + MixU::TOH - 1) / MixU::TOH;
+    mp.groups = C / MixU::CG;
+    const int n_sp = batch * mp.tiles_x * mp.tiles_y;
+    int per = (2 * h->num_sms) / mp.groups;             // two CTAs per SM
+    if (per < 1) per = 1;
+    if (per > n_sp) per = n_sp;
+    mp.ctas_per_group = per;
+    CUtensorMap tm;
+    int rc = make_tmap_chunked(h, &tm, x, batch, H, W, C, MixU::P, MixU::XH);
+    if (rc != FVHD_OK) return rc;
+    const dim3 grid((unsigned)(per * mp.groups));
+    *st = [=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+        return launch_k(repmixer_umma_kernel, grid, dim3(MixU::THREADS), MixU::SMEM, s, tm, mp);
+    };
     return FVHD_OK;
 }
 
@@ -613,7 +657,12 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
             // default: 16x16 tiles with the 7x7 on the tensor cores (mixer_tc.cuh).  FVHD_MIX_TILE selects the FMA-pipe variants
             // of dwconv.cuh instead: 'a' = their old automatic choice, '1' = 16x16/256 thr, '8' = 8x16/128 thr, '5' = 16x16/512 thr.
             const long ctas16 = (long)((W + 15) / 16) * ((H + 15) / 16) * (c / DW_CG) * batch;
-            bool small = false, wide = false, tc = true;
+            if (g_mixer_mode == 'u' && !getenv("FVHD_MIX_TILE")) {
+                Step ms;
+                if ((rc = make_mixer_umma_step(h, &ms, in, bf.Y, bf.Z, w3, b3, w7, b7, batch, H, W, c)) != FVHD_OK) return rc;
+                pl.add(ms, "repmixer_umma_kernel", U, 2.0 * Md * c * 58, 3.0 * Md * c * 2);
+            } else {
+            bool small = false, wide = false, tc = g_mixer_mode != 'f';
             { const char* e = getenv("FVHD_MIX_TILE");
               if (e && e[0] == 'a') { tc = false; small = ctas16 < 2L * h->num_sms; }
               else if (e && e[0] == '8') { tc = false; small = true; }
@@ -633,6 +682,8 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
                 if (small) return launch_k(repmixer_dw_kernel<8, 16, 128>, grid, dim3(128), MixCfgT<8, 16>::SMEM, s, tmx, y, z, w3, b3, w7, b7, H, W, c, tx);
                 return launch_k(repmixer_dw_kernel<16, 16, 256>, grid, dim3(256), MixCfgT<16, 16>::SMEM, s, tmx, y, z, w3, b3, w7, b7, H, W, c, tx);
             }, tc ? "repmixer_tc_kernel" : "repmixer_dw_kernel", U, 2.0 * Md * c * 58, 3.0 * Md * c * 2);
+            }
+            bf16 *y = bf.Y, *z = bf.Z;
             if (g_use_fused_mlp && c <= 192) {
                 if ((rc = add_fused_mlp_step(h, pl, U, p, z, y, out, M, c)) != FVHD_OK) return rc;
             } else if (g_use_cluster_mlp && c == MLPC_C && h->mlpc_clusters > 0 && (M + GEMM_BM - 1) / GEMM_BM <= 2 * h->mlpc_clusters) {
@@ -1286,6 +1337,21 @@ int fvhd_gemm(fvhd_handle h, void* stream, const void* A, const void* W, const v
     RunCtx ctx{};
     cudaError_t e = s(reinterpret_cast<cudaStream_t>(stream), ctx);
     if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "gemm launch failed: %s", cudaGetErrorString(e));
+    return FVHD_OK;
+}
+
+int fvhd_mixer(fvhd_handle h, void* stream, const void* x, const void* w3, const void* b3, const void* w7, const void* b7,
+               void* y, void* z, int batch, int H, int W, int C) {
+    if (!h) return FVHD_ERR_INVALID;
+    int rc = ensure_cuda(h);
+    if (rc != FVHD_OK) return rc;
+    if (!x || !w3 || !b3 || !w7 || !b7 || !y || !z || batch < 1 || H < 1 || W < 1) return fail(h, FVHD_ERR_INVALID, "fvhd_mixer: null operand or empty shape");
+    Step s;
+    if ((rc = make_mixer_umma_step(h, &s, (const bf16*)x, (bf16*)y, (bf16*)z, (const float*)w3, (const float*)b3, (const float*)w7,
+                                   (const float*)b7, batch, H, W, C)) != FVHD_OK) return rc;
+    RunCtx ctx{};
+    cudaError_t e = s(reinterpret_cast<cudaStream_t>(stream), ctx);
+    if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "mixer launch failed: %s", cudaGetErrorString(e));
     return FVHD_OK;
 }
 

@@ -253,6 +253,16 @@ class Engine:
                                        residual.data_ptr() if residual is not None else None, D.data_ptr(), M, N, K, int(act)), self.handle)
         return D
 
+    def mixer(self, x, w3, b3, w7, b7):
+        """(y, z) = (dw3x3(x) + b3, dw7x7(y) + b7) on the tcgen05 mixer kernel; x bf16 NHWC [B,H,W,C], weights fp32 tap-major."""
+        B, H, W, Cc = x.shape
+        y = torch.empty_like(x)
+        z = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            L.check(self.lib.fvhd_mixer(self.handle, C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream), x.data_ptr(), w3.data_ptr(),
+                                        b3.data_ptr(), w7.data_ptr(), b7.data_ptr(), y.data_ptr(), z.data_ptr(), B, H, W, Cc), self.handle)
+        return y, z
+
     def convffn(self, z, w1, b1, w2, b2, resid, trace=None):
         """resid + fc2(GELU(fc1(z) + b1)) + b2 on the fused ConvFFN kernels (z, resid [M,C] bf16; w1 [4C,C], w2 [C,4C] bf16;
         b1, b2 fp32; C in {96, 192, 384}).  `trace`: optional int64 CUDA tensor, 64 entries per CTA (C = 384 only)."""

@@ -98,11 +98,14 @@ def test_encode_images_1024_multi_pass_vs_oracle(packed, oracle1024_b3, tower_sd
     for i in range(5):                                             # per image: one bad image must not average out
         assert rel_l2(tokens[i].float(), want_t[i]) < E2E_TOL, i
         assert rel_l2(proj[i].float(), want_p[i]) < E2E_TOL, i
-    # the same five images one at a time give the same bits (batch slots / passes do not interact)
+    # the same images one at a time (batch-1 plan)
     eng1 = pkg.Engine(1024, 896, 2, 1).load(packed, dev)
     for i in (0, 4):
         _, p1 = eng1.forward(x[i:i + 1], False, True)
-        assert rel_l2(p1[0].float(), proj[i].float()) < 6e-3       # batch 1 uses the cluster ConvFFN (different summation order)
+        # batch 1 selects other kernels for stage 2 (cluster ConvFFN, f16 partial sums): same result up to the chain's amplification of
+        # rounding differences (measured 2e-2 through the 51 units; each path is within E2E_TOL of the oracle on its own)
+        assert rel_l2(p1[0].float(), proj[i].float()) < E2E_TOL
+        assert rel_l2(p1[0].float(), want_p[i]) < E2E_TOL
 
 
 def test_cluster_convffn_multi_tile_stress(dev):
@@ -206,3 +209,59 @@ def test_fused_all_gather_two_gpus(tmp_path):
     mp.spawn(_gather_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert torch.load(os.path.join(str(tmp_path), f"r{r}.pt"))["ok"], f"rank {r}"
+
+
+# ------------------------------------------------------------------ tcgen05 depthwise mixer (mixer_umma.cuh)
+def _mixer_ref(x_nhwc, w3, b3, w7, b7, round_weights):
+    """torch fp32 reference of the RepMixer depthwise pair; y is rounded to bf16 between the convs (as the kernel stores it)."""
+    import torch.nn.functional as F
+    C = x_nhwc.shape[-1]
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    if round_weights:
+        w3, w7 = w3.to(torch.bfloat16).float(), w7.to(torch.bfloat16).float()
+    k3 = w3.t().reshape(C, 1, 3, 3)
+    k7 = w7.t().reshape(C, 1, 7, 7)
+    y = F.conv2d(x, k3, b3, padding=1, groups=C)
+    yb = y.to(torch.bfloat16).float()
+    z = F.conv2d(yb, k7, b7, padding=3, groups=C)
+    return y.permute(0, 2, 3, 1), z.permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize("B,H,W,C", [
+    (1, 64, 64, 384),      # stage 2 at 1024 px
+    (2, 128, 128, 192),    # stage 1, batch 2
+    (1, 256, 256, 96),     # stage 0
+    (1, 16, 16, 384),      # stage 2 at 256 px: map smaller than the 16 x 32 tile
+    (3, 40, 24, 32),       # ragged in both directions, 2 channel groups, batch 3
+    (1, 96, 96, 48),       # 1536-px geometry (3 tiles across), 3 groups
+])
+def test_umma_mixer_vs_torch(dev, B, H, W, C):
+    eng = pkg.Engine(64, 0, 2, 1)
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + C)
+    x = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16)
+    w3 = torch.randn(9, C, generator=g) / 3.0
+    b3 = torch.randn(C, generator=g) * 0.1
+    w7 = torch.randn(49, C, generator=g) / 7.0
+    b7 = torch.randn(C, generator=g) * 0.1
+    y, z = eng.mixer(x.to(dev), w3.to(dev), b3.to(dev), w7.to(dev), b7.to(dev))
+    torch.cuda.synchronize()
+    yr, zr = _mixer_ref(x, w3, b3, w7, b7, round_weights=True)       # the kernel's own arithmetic: bf16 taps, fp32 accumulate
+    ye, ze = _mixer_ref(x, w3, b3, w7, b7, round_weights=False)      # exact fp32 taps (what the oracle computes)
+    ey, ez = rel_l2(y.float(), yr), rel_l2(z.float(), zr)
+    print(f"umma mixer {B}x{H}x{W}x{C}: y {ey:.2e} z {ez:.2e} | vs fp32 taps: y {rel_l2(y.float(), ye):.2e} z {rel_l2(z.float(), ze):.2e}")
+    assert torch.isfinite(y.float()).all() and torch.isfinite(z.float()).all()
+    assert ey < 3e-3 and ez < 4e-3, (ey, ez)                           # bf16 output rounding (y also feeds z)
+    assert rel_l2(y.float(), ye) < 5e-3 and rel_l2(z.float(), ze) < 6e-3
+
+
+def test_umma_mixer_identity_taps(dev):
+    """Centre taps = 1, everything else 0: y == x + b3, z == y + b7 exactly (bf16 in, fp32 accumulate, bf16 out)."""
+    eng = pkg.Engine(64, 0, 2, 1)
+    g = torch.Generator().manual_seed(1)
+    B, H, W, C = 1, 48, 80, 32
+    x = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16)
+    w3 = torch.zeros(9, C); w3[4] = 1.0
+    w7 = torch.zeros(49, C); w7[24] = 1.0
+    zb = torch.zeros(C)
+    y, z = eng.mixer(x.to(dev), w3.to(dev), zb.to(dev), w7.to(dev), zb.to(dev))
+    assert torch.equal(y.cpu(), x) and torch.equal(z.cpu(), x)
