@@ -104,6 +104,14 @@ int fvhd_forward_strided(fvhd_handle h, void* stream, const void* images, int im
 int fvhd_forward_gather(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch,
                         void* local_out, void* const* peer_out, int n_peers);
 
+/* encode_images whose projector epilogue stores image i's [N, H] token block (dense rows) at dst_per_image[i]: the general
+ * splice of prepare_inputs_labels_for_multimodal (llava_arch.py:233-271) -- several <image> tokens per sample, a different
+ * position in every sample, ragged sequence lengths -- with no intermediate feature tensor and no torch.cat.  The host
+ * computes the destinations (Python: glue.prepare_inputs_embeds).  `dst_per_image`: HOST array of `batch` device pointers,
+ * 16-B aligned; requires a projector and cfg.max_batch <= 64. */
+int fvhd_forward_scatter(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch,
+                         void* const* dst_per_image);
+
 /* Same call with HOST buffers: H2D of the images, the forward, D2H of the result, one stream sync.
  * `host_out` receives `projected` when the plan has a projector, else `tokens` (bf16). */
 int fvhd_encode_images_host(fvhd_handle h, void* stream, const void* host_images, int img_dtype, int batch,

@@ -17,7 +17,8 @@ from .packer import pack_tower, pack_projector  # noqa: F401
 from .engine import Engine  # noqa: F401
 from .tower import FastViTHDVisionTower, build_vision_tower  # noqa: F401
 from .projector import FastVLMProjector, build_vision_projector  # noqa: F401
-from .glue import encode_images, splice_visual_tokens, EncodeImagesMixin, patch_llava  # noqa: F401
+from .glue import (encode_images, splice_visual_tokens, splice_layout, prepare_inputs_embeds, EncodeImagesMixin, patch_llava,  # noqa: F401
+                   IMAGE_TOKEN_INDEX)
 from .checkpoint import read_state_dicts, load_pretrained  # noqa: F401
 from .preprocess import (process_images, preprocess_into, resample_coeffs, process_anyres_image, select_best_resolution,  # noqa: F401
                          get_anyres_image_grid_shape, anyres_geometry)

@@ -799,10 +799,12 @@ int run_steps(fvhd_handle h, Plan& pl, int s0, int s1, cudaStream_t st, const Ru
 }
 
 int set_io(fvhd_handle h, Plan& pl, cudaStream_t st, const void* images, void* final_out, void* tokens_out, long long final_image_stride,
-           const PeerList* peers = nullptr) {
+           const PeerList* peers = nullptr, const ScatterList* scatter = nullptr) {
     PeerList pl_peers{};
     if (peers) pl_peers = *peers;
-    cudaError_t e = launch_k(set_io_kernel, dim3(1), dim3(1), 0, st, pl.io, images, final_out, tokens_out, final_image_stride, pl_peers);
+    ScatterList sc{};
+    if (scatter) sc = *scatter;
+    cudaError_t e = launch_k(set_io_kernel, dim3(1), dim3(FVHD_MAX_SCATTER), 0, st, pl.io, images, final_out, tokens_out, final_image_stride, pl_peers, sc);
     if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "set_io_kernel launch failed: %s", cudaGetErrorString(e));
     return FVHD_OK;
 }
@@ -992,7 +994,7 @@ int fvhd_launches_per_forward(fvhd_handle h, int batch) {
 
 namespace {
 int forward_impl(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch, void* tokens, void* projected,
-                 long long out_image_stride, void* const* peer_out, int n_peers);
+                 long long out_image_stride, void* const* peer_out, int n_peers, void* const* scatter = nullptr);
 }
 
 extern "C" {
@@ -1018,11 +1020,21 @@ int fvhd_forward_gather(fvhd_handle h, void* stream, const void* images, int img
     return forward_impl(h, stream, images, img_dtype, batch, nullptr, local_out, 0, peer_out, n_peers);
 }
 
+int fvhd_forward_scatter(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch, void* const* dst_per_image) {
+    if (!h) return FVHD_ERR_INVALID;
+    if (h->cfg.projector_hidden <= 0) return fail(h, FVHD_ERR_INVALID, "fvhd_forward_scatter needs a plan with a projector");
+    if (!dst_per_image) return fail(h, FVHD_ERR_INVALID, "dst_per_image is null");
+    if (h->cfg.max_batch > FVHD_MAX_SCATTER) return fail(h, FVHD_ERR_INVALID, "fvhd_forward_scatter supports max_batch <= %d", FVHD_MAX_SCATTER);
+    for (int i = 0; i < batch; ++i)
+        if (!dst_per_image[i] || ((uintptr_t)dst_per_image[i] & 15)) return fail(h, FVHD_ERR_INVALID, "dst_per_image[%d] must be a non-null, 16-B aligned device pointer", i);
+    return forward_impl(h, stream, images, img_dtype, batch, nullptr, dst_per_image[0], 0, nullptr, 0, dst_per_image);
+}
+
 }  // extern "C"
 
 namespace {
 int forward_impl(fvhd_handle h, void* stream, const void* images, int img_dtype, int batch, void* tokens, void* projected,
-                 long long out_image_stride, void* const* peer_out, int n_peers) {
+                 long long out_image_stride, void* const* peer_out, int n_peers, void* const* scatter) {
     int rc = check_ready(h, batch);
     if (rc != FVHD_OK) return rc;
     if (!images) return fail(h, FVHD_ERR_INVALID, "images is null");
@@ -1057,7 +1069,9 @@ int forward_impl(fvhd_handle h, void* stream, const void* images, int img_dtype,
             PeerList peers{};
             peers.n = n_peers;
             for (int i = 0; i < n_peers; ++i) peers.p[i] = reinterpret_cast<uint8_t*>(peer_out[i]) + (size_t)b0 * prj_stride;
-            if ((rc = set_io(h, *pl, st, img, prj_dst, tok_dst, final_stride, &peers)) != FVHD_OK) return rc;
+            ScatterList sc{};
+            if (scatter) { sc.n = bc; for (int i = 0; i < bc; ++i) sc.p[i] = scatter[b0 + i]; }
+            if ((rc = set_io(h, *pl, st, img, prj_dst, tok_dst, final_stride, &peers, &sc)) != FVHD_OK) return rc;
             if ((rc = run_forward(h, *pl, st, ctx, pl->unit_steps[last_unit].second, tok_dst ? pl->unit_out[tok_unit] : nullptr,
                                   (size_t)bc * tok_stride)) != FVHD_OK) return rc;
         } else {

@@ -250,9 +250,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 drow = p.D + (size_t)row * p.ldd;
             } else {        // caller memory: image b's tokens start at final_out + b * final_image_stride
                 const int bi = row / p.rows_per_image;
-                doff = (size_t)bi * (size_t)p.io->final_image_stride + (size_t)(row - bi * p.rows_per_image) * p.ldd;
-                drow = reinterpret_cast<bf16*>(p.io->final_out) + doff;
-                npeers = p.io->n_peers;
+                if (p.io->scatter_n > 0) {     // every image has its own destination block (ragged / multi-<image> splice)
+                    drow = reinterpret_cast<bf16*>(p.io->scatter[bi < p.io->scatter_n ? bi : 0]) + (size_t)(row - bi * p.rows_per_image) * p.ldd;
+                } else {
+                    doff = (size_t)bi * (size_t)p.io->final_image_stride + (size_t)(row - bi * p.rows_per_image) * p.ldd;
+                    drow = reinterpret_cast<bf16*>(p.io->final_out) + doff;
+                    npeers = p.io->n_peers;
+                }
             }
             const bf16* rrow = p.residual ? p.residual + (size_t)row * p.ldr : nullptr;
             // ---- everything that does not depend on the accumulator is fetched BEFORE waiting for it: the bias of this

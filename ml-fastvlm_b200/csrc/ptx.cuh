@@ -14,6 +14,7 @@ typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;
 
 constexpr int FVHD_MAX_PEERS = 8;
+constexpr int FVHD_MAX_SCATTER = 64;
 
 // Caller-owned pointers of one forward call, kept in device memory so that the launch sequence itself is
 // static (replayable as a CUDA graph): written by set_io_kernel, read by the first and last kernels.
@@ -28,6 +29,10 @@ struct IoBlock {
     // runs the tcgen05 tiles), so no separate collective pass follows the projector.
     int n_peers;
     void* peer_out[FVHD_MAX_PEERS];
+    // Scatter (multi-<image> / ragged splice, llava_arch.py:233-271): when scatter_n > 0 image b's token block goes to
+    // scatter[b] (dense [N, H] rows) instead of final_out + b * final_image_stride.
+    int scatter_n;
+    void* scatter[FVHD_MAX_SCATTER];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -452,15 +452,21 @@ se_expand_scale_gelu_kernel(const bf16* __restrict__ c, const float* __restrict_
 
 // ====================================================================== IO plumbing
 struct PeerList { int n; void* p[FVHD_MAX_PEERS]; };
-__global__ void set_io_kernel(IoBlock* io, const void* images, void* final_out, void* tokens_out, long long final_image_stride, const PeerList peers) {
+struct ScatterList { int n; void* p[FVHD_MAX_SCATTER]; };
+__global__ void set_io_kernel(IoBlock* io, const void* images, void* final_out, void* tokens_out, long long final_image_stride, const PeerList peers,
+                              const ScatterList sc) {
     pdl_launch_dependents();
     pdl_wait();                 // the previous forward's last kernels may still be reading the block
-    io->images = images;
-    io->final_out = final_out;
-    io->tokens_out = tokens_out;
-    io->final_image_stride = final_image_stride;
-    io->n_peers = peers.n;
-    for (int i = 0; i < FVHD_MAX_PEERS; ++i) io->peer_out[i] = i < peers.n ? peers.p[i] : nullptr;
+    if (threadIdx.x == 0) {
+        io->images = images;
+        io->final_out = final_out;
+        io->tokens_out = tokens_out;
+        io->final_image_stride = final_image_stride;
+        io->n_peers = peers.n;
+        for (int i = 0; i < FVHD_MAX_PEERS; ++i) io->peer_out[i] = i < peers.n ? peers.p[i] : nullptr;
+        io->scatter_n = sc.n;
+    }
+    if (threadIdx.x < FVHD_MAX_SCATTER) io->scatter[threadIdx.x] = (int)threadIdx.x < sc.n ? sc.p[threadIdx.x] : nullptr;
 }
 // tokens (workspace) -> caller buffer, 16 B per thread-iteration
 __global__ void __launch_bounds__(256)

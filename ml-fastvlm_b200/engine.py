@@ -180,6 +180,20 @@ class Engine:
                                                      host_out.data_ptr()), self.handle)
         return host_out
 
+    def forward_scatter(self, images, dst_ptrs):
+        """encode_images with image i's projected [N, H] block stored at device address dst_ptrs[i] (ints; dense rows): the
+        general multi-<image> / ragged splice (llava_arch.py:233-271) as the projector's store.  The caller guarantees every
+        destination is a writable bf16 region of N*H elements on this device."""
+        if self.hidden <= 0:
+            raise L.FvhdError("forward_scatter needs a plan with a projector")
+        images = self._check_images(images, self.device)
+        B = images.shape[0]
+        if len(dst_ptrs) != B:
+            raise L.FvhdError(f"{B} images but {len(dst_ptrs)} destinations")
+        arr = (C.c_void_p * B)(*[C.c_void_p(int(p)) for p in dst_ptrs])
+        with torch.cuda.device(self.device):
+            L.check(self.lib.fvhd_forward_scatter(self.handle, self._stream(), images.data_ptr(), _img_dtype(images), B, arr), self.handle)
+
     def forward_gather(self, images, local_out, peer_ptrs):
         """encode_images of this rank's shard with the all-gather fused into the projector's store: the projected tokens
         are written to `local_out` ([b,N,H] bf16 view of this rank's slot in its own gathered buffer) AND, by the same
