@@ -175,6 +175,11 @@ int fvhd_debug_mixer_trace(void* dev_buf_8_u64_per_cta);
 int fvhd_gemm(fvhd_handle h, void* stream, const void* A, const void* W, const void* bias, const void* residual,
               void* D, int M, int N, int K, int act);
 
+/* Test entry: the second-generation fused ConvFFN kernel (convffn.cuh; one CTA per 128-row tile, packed-half GELU, f16 hidden),
+ * same operands as fvhd_convffn, C in {96, 192, 384}, any M. */
+int fvhd_convffn2(fvhd_handle h, void* stream, const void* z, const void* w1, const void* b1, const void* w2, const void* b2,
+                  const void* resid, void* out, int M, int C);
+
 /* Test entry: the RepMixer depthwise pair of one block on the tcgen05 mixer kernel (mixer_umma.cuh), mci.py:808-811 + :921:
  *   y = dw3x3(x) + b3,  z = dw7x7(y) + b7;  x, y, z device bf16 NHWC [B,H,W,C]; w3 [9][C], w7 [49][C], b3, b7 [C] fp32 (tap-major,
  *   BN folded).  C % 16 == 0. */

@@ -23,6 +23,7 @@
 #include "stem_attn_se.cuh"
 #include "mixer_tc.cuh"
 #include "mixer_umma.cuh"
+#include "convffn.cuh"
 
 using namespace fvhd;
 
@@ -270,7 +271,9 @@ int g_gemm_max_cs = 1;        // FVHD_GEMM_CS=1|2|4 caps the GEMM cluster size. 
                               // the limit and multicast only reduces L2 reads -- measured no gain (profiles/r01_f_summary.md)
 bool g_use_cluster_mlp = true; // FVHD_NO_CLUSTER_MLP=1: stage-2 (C = 384) ConvFFN as two GEMM launches instead of the 4-CTA-cluster kernel
 bool g_use_fused_mlp = true;  // FVHD_NO_FUSED_MLP=1: ConvFFN as two GEMM launches (reference path of the bit-exactness test)
-char g_mixer_mode = 't';       // FVHD_MIXER=u: tcgen05 mixer (mixer_umma.cuh); t: mma.sync 7x7 (mixer_tc.cuh); f: FMA pipes (dwconv.cuh)
+const int g_convffn_default = 1;
+int g_convffn_gen = 1;         // FVHD_CONVFFN=2: second-generation fused ConvFFN kernel (convffn.cuh); 1: mlp_fused / two GEMMs
+char g_mixer_mode = 'u';       // FVHD_MIXER=u: tcgen05 mixer (mixer_umma.cuh, default); t: mma.sync 7x7 (mixer_tc.cuh); f: FMA pipes (dwconv.cuh)
 unsigned long long* g_gemm_trace = nullptr;   // fvhd_debug_gemm_trace: device buffer, 16 stamps per CTA
 int g_force_bn = 0;                            // fvhd_debug_gemm_trace: force the N tile (0 = cost model)
 template <typename... KArgs, typename... Args>
@@ -347,7 +350,11 @@ int ensure_cuda(fvhd_handle h) {
     CUDA_TRY(h, set_smem(repmixer_dw_kernel<16, 16, 512, 6, 4, 2>, MixCfgT<16, 16>::SMEM));
     CUDA_TRY(h, set_smem(repmixer_tc_kernel, MixTc::SMEM));
     CUDA_TRY(h, set_smem(repmixer_umma_kernel, MixU::SMEM));
-    { const char* e = getenv("FVHD_MIXER"); if (e && e[0]) g_mixer_mode = e[0]; }
+    { const char* e = getenv("FVHD_MIXER"); g_mixer_mode = (e && e[0]) ? e[0] : 'u'; }
+    { const char* e = getenv("FVHD_CONVFFN"); g_convffn_gen = (e && e[0] == '2') ? 2 : (e && e[0] == '1') ? 1 : g_convffn_default; }
+    CUDA_TRY(h, set_smem(convffn_tcgen05_kernel<96>, CfCfg<96>::SMEM));
+    CUDA_TRY(h, set_smem(convffn_tcgen05_kernel<192>, CfCfg<192>::SMEM));
+    CUDA_TRY(h, set_smem(convffn_tcgen05_kernel<384>, CfCfg<384>::SMEM));
     CUDA_TRY(h, set_smem(dwconv_kernel<7, 1, 1, 0, 16, 16, 8>, DwCfg<7, 1, 1, 16, 16>::SMEM));
     CUDA_TRY(h, set_smem(dwconv_kernel<7, 2, 2, 1, 8, 8, 4>, DwCfg<7, 2, 2, 8, 8>::SMEM));
     CUDA_TRY(h, set_smem(dwconv_kernel<3, 1, 2, 0, 16, 16, 8>, DwCfg<3, 1, 2, 16, 16>::SMEM));
@@ -586,6 +593,40 @@ int add_fused_mlp_step(fvhd_handle h, Plan& pl, int unit, const std::string& p, 
     return FVHD_OK;
 }
 
+// Second-generation fused ConvFFN (convffn.cuh): one CTA per 128-pixel tile, 16 epilogue warps, packed-half GELU, C in {96, 192, 384}.
+template <int C>
+int make_convffn2_step_t(fvhd_handle h, Step* st, const bf16* z, const bf16* w1, const float* b1, const bf16* w2, const float* b2,
+                         const bf16* resid, bf16* out, int M) {
+    MlpParams mp{};
+    mp.M = M; mp.C = C; mp.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+    mp.b1 = b1; mp.b2 = b2; mp.resid = resid; mp.D = out;
+    CUtensorMap tz, tw1, tw2;
+    int rc;
+    if ((rc = make_tmap(h, &tz, z, M, C, C, GEMM_BM)) != FVHD_OK) return rc;
+    if ((rc = make_tmap(h, &tw1, w1, 4 * C, C, C, MLP_NH)) != FVHD_OK) return rc;
+    if ((rc = make_tmap(h, &tw2, w2, C, 4 * C, 4 * C, CfCfg<C>::N2)) != FVHD_OK) return rc;
+    const dim3 grid((unsigned)(mp.tiles_m < h->num_sms ? mp.tiles_m : h->num_sms));
+    const size_t smem = CfCfg<C>::SMEM;
+    *st = [=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+        return launch_k(convffn_tcgen05_kernel<C>, grid, dim3(CF_THREADS), smem, s, tz, tw1, tw2, mp);
+    };
+    return FVHD_OK;
+}
+int make_convffn2_step(fvhd_handle h, Step* st, const bf16* z, const bf16* w1, const float* b1, const bf16* w2, const float* b2,
+                       const bf16* resid, bf16* out, int M, int c) {
+    if (c == 96) return make_convffn2_step_t<96>(h, st, z, w1, b1, w2, b2, resid, out, M);
+    if (c == 192) return make_convffn2_step_t<192>(h, st, z, w1, b1, w2, b2, resid, out, M);
+    if (c == 384) return make_convffn2_step_t<384>(h, st, z, w1, b1, w2, b2, resid, out, M);
+    return fail(h, FVHD_ERR_INVALID, "convffn_tcgen05_kernel exists for C in {96, 192, 384}, got %d", c);
+}
+int add_convffn2_step(fvhd_handle h, Plan& pl, int unit, const std::string& p, const bf16* z, const bf16* resid, bf16* out, int M, int c) {
+    Step st;
+    int rc = make_convffn2_step(h, &st, z, WB(h, p + "fc1.w"), WF(h, p + "fc1.b"), WB(h, p + "fc2.w"), WF(h, p + "fc2.b"), resid, out, M, c);
+    if (rc != FVHD_OK) return rc;
+    pl.add(st, "convffn_tcgen05_kernel", unit, 2.0 * gemm_flops(M, 4 * c, c), 2.0 * (3.0 * M * c + 8.0 * c * c) + 20.0 * c);
+    return FVHD_OK;
+}
+
 // Stage-2 ConvFFN (C = 384): one 4-CTA cluster per 128-pixel tile, hidden split across the cluster, DSMEM reduction.
 int make_cluster_mlp_step(fvhd_handle h, Step* st, const bf16* z, const bf16* w1, const float* b1, const bf16* w2, const float* b2,
                           const bf16* resid, bf16* out, int M, unsigned long long* trace) {
@@ -684,7 +725,12 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
             }, tc ? "repmixer_tc_kernel" : "repmixer_dw_kernel", U, 2.0 * Md * c * 58, 3.0 * Md * c * 2);
             }
             bf16 *y = bf.Y, *z = bf.Z;
-            if (g_use_fused_mlp && c <= 192) {
+            const bool few_tiles = c == MLPC_C && g_use_cluster_mlp && h->mlpc_clusters > 0 && (M + GEMM_BM - 1) / GEMM_BM <= 2 * h->mlpc_clusters;
+            if (g_use_fused_mlp && g_convffn_gen == 2 && !few_tiles) {
+                // second-generation single-CTA kernel: every C, any batch (stage 2 at batch <= 2 keeps the 4-CTA cluster kernel:
+                // 32 tiles per image cannot fill 148 SMs one tile per CTA)
+                if ((rc = add_convffn2_step(h, pl, U, p, z, y, out, M, c)) != FVHD_OK) return rc;
+            } else if (g_use_fused_mlp && c <= 192) {
                 if ((rc = add_fused_mlp_step(h, pl, U, p, z, y, out, M, c)) != FVHD_OK) return rc;
             } else if (g_use_cluster_mlp && c == MLPC_C && h->mlpc_clusters > 0 && (M + GEMM_BM - 1) / GEMM_BM <= 2 * h->mlpc_clusters) {
                 // small batches only: beyond two tiles per resident cluster the two plain GEMMs fill the machine better
@@ -972,7 +1018,7 @@ int fvhd_launches_per_forward(fvhd_handle h, int batch) {
             case 0: steps += 2; break;
             case 1: {
                 const int tiles_m = (bc * u.hout * u.wout + GEMM_BM - 1) / GEMM_BM;
-                steps += ((g_use_fused_mlp && u.cin <= 192) ||
+                steps += ((g_use_fused_mlp && (u.cin <= 192 || g_convffn_gen == 2)) ||
                           (g_use_cluster_mlp && u.cin == MLPC_C && h->mlpc_clusters > 0 && tiles_m <= 2 * h->mlpc_clusters)) ? 2 : 3;
                 break;
             }
@@ -1351,6 +1397,21 @@ int fvhd_gemm(fvhd_handle h, void* stream, const void* A, const void* W, const v
     RunCtx ctx{};
     cudaError_t e = s(reinterpret_cast<cudaStream_t>(stream), ctx);
     if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "gemm launch failed: %s", cudaGetErrorString(e));
+    return FVHD_OK;
+}
+
+int fvhd_convffn2(fvhd_handle h, void* stream, const void* z, const void* w1, const void* b1, const void* w2, const void* b2,
+                  const void* resid, void* out, int M, int C) {
+    if (!h) return FVHD_ERR_INVALID;
+    int rc = ensure_cuda(h);
+    if (rc != FVHD_OK) return rc;
+    if (!z || !w1 || !b1 || !w2 || !b2 || !resid || !out || M <= 0) return fail(h, FVHD_ERR_INVALID, "fvhd_convffn2: null operand or M <= 0");
+    Step s;
+    if ((rc = make_convffn2_step(h, &s, (const bf16*)z, (const bf16*)w1, (const float*)b1, (const bf16*)w2, (const float*)b2,
+                                 (const bf16*)resid, (bf16*)out, M, C)) != FVHD_OK) return rc;
+    RunCtx ctx{};
+    cudaError_t e = s(reinterpret_cast<cudaStream_t>(stream), ctx);
+    if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "convffn2 launch failed: %s", cudaGetErrorString(e));
     return FVHD_OK;
 }
 

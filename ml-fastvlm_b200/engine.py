@@ -267,6 +267,15 @@ class Engine:
                                        residual.data_ptr() if residual is not None else None, D.data_ptr(), M, N, K, int(act)), self.handle)
         return D
 
+    def convffn2(self, z, w1, b1, w2, b2, resid):
+        """Same operands as convffn(), on the second-generation fused kernel (convffn.cuh)."""
+        M, Cc = z.shape
+        out = torch.empty(M, Cc, dtype=torch.bfloat16, device=z.device)
+        with torch.cuda.device(z.device):
+            L.check(self.lib.fvhd_convffn2(self.handle, C.c_void_p(torch.cuda.current_stream(z.device).cuda_stream), z.data_ptr(), w1.data_ptr(),
+                                           b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), resid.data_ptr(), out.data_ptr(), M, Cc), self.handle)
+        return out
+
     def mixer(self, x, w3, b3, w7, b7):
         """(y, z) = (dw3x3(x) + b3, dw7x7(y) + b7) on the tcgen05 mixer kernel; x bf16 NHWC [B,H,W,C], weights fp32 tap-major."""
         B, H, W, Cc = x.shape
