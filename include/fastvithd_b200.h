@@ -176,8 +176,9 @@ int fvhd_gemm(fvhd_handle h, void* stream, const void* A, const void* W, const v
               void* D, int M, int N, int K, int act);
 
 /* Test entry: the second-generation fused ConvFFN kernel (convffn.cuh; one CTA per 128-row tile, packed-half GELU, f16 hidden),
- * same operands as fvhd_convffn, C in {96, 192, 384}, any M. */
-int fvhd_convffn2(fvhd_handle h, void* stream, const void* z, const void* w1, const void* b1, const void* w2, const void* b2,
+ * same operands as fvhd_convffn except w2: f16 [C, 4C] when w2_is_f16 (the production format, packer `fc2.wh`), else bf16;
+ * C in {96, 192, 384}, any M. */
+int fvhd_convffn_half(fvhd_handle h, void* stream, const void* z, const void* w1, const void* b1, const void* w2, int w2_is_f16, const void* b2,
                   const void* resid, void* out, int M, int C);
 
 /* Test entry: the RepMixer depthwise pair of one block on the tcgen05 mixer kernel (mixer_umma.cuh), mci.py:808-811 + :921:

@@ -7,8 +7,8 @@
 // issue-bound at IPC 0.36 per scheduler with only two epilogue warps to pick from.  Changes:
 //   * SIXTEEN epilogue warps (four per scheduler, one 16-column slice of the chunk each) instead of eight;
 //   * GELU in packed half precision (f16x2: HMUL2 / HFMA2 / one tanh.approx.f16x2 per TWO elements) and H kept as f16 -- 11
-//     significand bits, three more than the bf16 H of the first generation; MMA2 multiplies f16 H by bf16 W2 (kind::f16
-//     takes the two operand formats independently);
+//     significand bits, three more than the bf16 H of the first generation; MMA2 multiplies it by an f16 copy of W2 (packer:
+//     `fc2.wh`; a mixed f16 x bf16 tcgen05.mma raised an illegal-instruction error on B200);
 //   * the MMA warp runs warp-uniformly (role index broadcast by shfl, `elect_one` only on the tcgen05 instructions), so the
 //     descriptors stay in uniform registers and the issue loop is back-to-back UTCHMMA;
 //   * C = 384 in ONE CTA: acc2 = 384 TMEM columns as two N = 192 halves, half-chunk weight slots (as the cluster kernel),
@@ -165,7 +165,7 @@ convffn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
     } else if (warp == 1) {
         // ---------------- MMA issuer (whole warp, uniform; one elected lane issues)
         const uint32_t idesc1 = umma_idesc_f16bf16(1, 1, GEMM_BM, MLP_NH);           // z (bf16) x W1 (bf16)
-        const uint32_t idesc2 = umma_idesc_f16bf16(0, 1, GEMM_BM, (uint32_t)N2);     // H (f16) x W2 (bf16)
+        const uint32_t idesc2 = umma_idesc_f16bf16(0, p.w2_f16 ? 0u : 1u, GEMM_BM, (uint32_t)N2);     // H (f16) x W2 (f16 copy; bf16 = mixed formats, test only)
         const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint64_t dz0 = umma_desc_sw128(smem_u32(smemZ));
         const uint64_t dh0 = umma_desc_sw128(smem_u32(smemH));

@@ -120,12 +120,13 @@ int fail(fvhd_handle h, int code, const char* fmt, ...) {
 
 void add_spec(fvhd_handle h, const std::string& n, int dt, int64_t numel) { h->specs.push_back({n, dt, numel}); }
 
-void add_convffn_specs(fvhd_handle h, const std::string& p, int c) {
+void add_convffn_specs(fvhd_handle h, const std::string& p, int c, bool f16_fc2 = false) {
     add_spec(h, p + "dw.w", FVHD_F32, 49LL * c);
     add_spec(h, p + "dw.b", FVHD_F32, c);
     add_spec(h, p + "fc1.w", FVHD_BF16, 4LL * c * c);
     add_spec(h, p + "fc1.b", FVHD_F32, 4LL * c);
     add_spec(h, p + "fc2.w", FVHD_BF16, 4LL * c * c);
+    if (f16_fc2) add_spec(h, p + "fc2.wh", FVHD_F16, 4LL * c * c);      // f16 copy of fc2.w for the f16-hidden fused ConvFFN kernel (convffn.cuh)
     add_spec(h, p + "fc2.b", FVHD_F32, c);
 }
 
@@ -184,7 +185,7 @@ void build_arch(fvhd_handle h) {
                 add_spec(h, u.prefix + "qkv.w", FVHD_BF16, 3LL * c * c);
                 add_spec(h, u.prefix + "proj.w", FVHD_BF16, (int64_t)c * c); add_spec(h, u.prefix + "proj.b", FVHD_F32, c);
             }
-            add_convffn_specs(h, u.prefix, c);
+            add_convffn_specs(h, u.prefix, c, i < 3);
             u.flops = 2 * macs; u.min_bytes = 4.0 * px * c + wbytes;
             h->units.push_back(u);
         }
@@ -273,7 +274,8 @@ bool g_use_cluster_mlp = true; // FVHD_NO_CLUSTER_MLP=1: stage-2 (C = 384) ConvF
 bool g_use_fused_mlp = true;  // FVHD_NO_FUSED_MLP=1: ConvFFN as two GEMM launches (reference path of the bit-exactness test)
 const int g_convffn_default = 1;
 int g_convffn_gen = 1;         // FVHD_CONVFFN=2: second-generation fused ConvFFN kernel (convffn.cuh); 1: mlp_fused / two GEMMs
-char g_mixer_mode = 'u';       // FVHD_MIXER=u: tcgen05 mixer (mixer_umma.cuh, default); t: mma.sync 7x7 (mixer_tc.cuh); f: FMA pipes (dwconv.cuh)
+char g_mixer_mode = 't';       // FVHD_MIXER=t: mma.sync 7x7 (mixer_tc.cuh, default); u: tcgen05 diagonal-tap mixer (mixer_umma.cuh: correct, but
+                               // smem-A-read bound -- 602 vs 434 us/img at batch 32, profiles/r02_*); f: FMA pipes (dwconv.cuh)
 unsigned long long* g_gemm_trace = nullptr;   // fvhd_debug_gemm_trace: device buffer, 16 stamps per CTA
 int g_force_bn = 0;                            // fvhd_debug_gemm_trace: force the N tile (0 = cost model)
 template <typename... KArgs, typename... Args>
@@ -350,7 +352,7 @@ int ensure_cuda(fvhd_handle h) {
     CUDA_TRY(h, set_smem(repmixer_dw_kernel<16, 16, 512, 6, 4, 2>, MixCfgT<16, 16>::SMEM));
     CUDA_TRY(h, set_smem(repmixer_tc_kernel, MixTc::SMEM));
     CUDA_TRY(h, set_smem(repmixer_umma_kernel, MixU::SMEM));
-    { const char* e = getenv("FVHD_MIXER"); g_mixer_mode = (e && e[0]) ? e[0] : 'u'; }
+    { const char* e = getenv("FVHD_MIXER"); g_mixer_mode = (e && e[0]) ? e[0] : 't'; }
     { const char* e = getenv("FVHD_CONVFFN"); g_convffn_gen = (e && e[0] == '2') ? 2 : (e && e[0] == '1') ? 1 : g_convffn_default; }
     CUDA_TRY(h, set_smem(convffn_tcgen05_kernel<96>, CfCfg<96>::SMEM));
     CUDA_TRY(h, set_smem(convffn_tcgen05_kernel<192>, CfCfg<192>::SMEM));
@@ -595,10 +597,11 @@ int add_fused_mlp_step(fvhd_handle h, Plan& pl, int unit, const std::string& p, 
 
 // Second-generation fused ConvFFN (convffn.cuh): one CTA per 128-pixel tile, 16 epilogue warps, packed-half GELU, C in {96, 192, 384}.
 template <int C>
-int make_convffn2_step_t(fvhd_handle h, Step* st, const bf16* z, const bf16* w1, const float* b1, const bf16* w2, const float* b2,
+int make_convffn2_step_t(fvhd_handle h, Step* st, const bf16* z, const bf16* w1, const float* b1, const void* w2, int w2_f16, const float* b2,
                          const bf16* resid, bf16* out, int M) {
     MlpParams mp{};
     mp.M = M; mp.C = C; mp.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+    mp.w2_f16 = w2_f16;
     mp.b1 = b1; mp.b2 = b2; mp.resid = resid; mp.D = out;
     CUtensorMap tz, tw1, tw2;
     int rc;
@@ -612,16 +615,16 @@ int make_convffn2_step_t(fvhd_handle h, Step* st, const bf16* z, const bf16* w1,
     };
     return FVHD_OK;
 }
-int make_convffn2_step(fvhd_handle h, Step* st, const bf16* z, const bf16* w1, const float* b1, const bf16* w2, const float* b2,
+int make_convffn2_step(fvhd_handle h, Step* st, const bf16* z, const bf16* w1, const float* b1, const void* w2, int w2_f16, const float* b2,
                        const bf16* resid, bf16* out, int M, int c) {
-    if (c == 96) return make_convffn2_step_t<96>(h, st, z, w1, b1, w2, b2, resid, out, M);
-    if (c == 192) return make_convffn2_step_t<192>(h, st, z, w1, b1, w2, b2, resid, out, M);
-    if (c == 384) return make_convffn2_step_t<384>(h, st, z, w1, b1, w2, b2, resid, out, M);
+    if (c == 96) return make_convffn2_step_t<96>(h, st, z, w1, b1, w2, w2_f16, b2, resid, out, M);
+    if (c == 192) return make_convffn2_step_t<192>(h, st, z, w1, b1, w2, w2_f16, b2, resid, out, M);
+    if (c == 384) return make_convffn2_step_t<384>(h, st, z, w1, b1, w2, w2_f16, b2, resid, out, M);
     return fail(h, FVHD_ERR_INVALID, "convffn_tcgen05_kernel exists for C in {96, 192, 384}, got %d", c);
 }
 int add_convffn2_step(fvhd_handle h, Plan& pl, int unit, const std::string& p, const bf16* z, const bf16* resid, bf16* out, int M, int c) {
     Step st;
-    int rc = make_convffn2_step(h, &st, z, WB(h, p + "fc1.w"), WF(h, p + "fc1.b"), WB(h, p + "fc2.w"), WF(h, p + "fc2.b"), resid, out, M, c);
+    int rc = make_convffn2_step(h, &st, z, WB(h, p + "fc1.w"), WF(h, p + "fc1.b"), h->wptr.at(p + "fc2.wh"), 1, WF(h, p + "fc2.b"), resid, out, M, c);
     if (rc != FVHD_OK) return rc;
     pl.add(st, "convffn_tcgen05_kernel", unit, 2.0 * gemm_flops(M, 4 * c, c), 2.0 * (3.0 * M * c + 8.0 * c * c) + 20.0 * c);
     return FVHD_OK;
@@ -1400,14 +1403,14 @@ int fvhd_gemm(fvhd_handle h, void* stream, const void* A, const void* W, const v
     return FVHD_OK;
 }
 
-int fvhd_convffn2(fvhd_handle h, void* stream, const void* z, const void* w1, const void* b1, const void* w2, const void* b2,
+int fvhd_convffn_half(fvhd_handle h, void* stream, const void* z, const void* w1, const void* b1, const void* w2, int w2_is_f16, const void* b2,
                   const void* resid, void* out, int M, int C) {
     if (!h) return FVHD_ERR_INVALID;
     int rc = ensure_cuda(h);
     if (rc != FVHD_OK) return rc;
-    if (!z || !w1 || !b1 || !w2 || !b2 || !resid || !out || M <= 0) return fail(h, FVHD_ERR_INVALID, "fvhd_convffn2: null operand or M <= 0");
+    if (!z || !w1 || !b1 || !w2 || !b2 || !resid || !out || M <= 0) return fail(h, FVHD_ERR_INVALID, "fvhd_convffn_half: null operand or M <= 0");
     Step s;
-    if ((rc = make_convffn2_step(h, &s, (const bf16*)z, (const bf16*)w1, (const float*)b1, (const bf16*)w2, (const float*)b2,
+    if ((rc = make_convffn2_step(h, &s, (const bf16*)z, (const bf16*)w1, (const float*)b1, w2, w2_is_f16, (const float*)b2,
                                  (const bf16*)resid, (bf16*)out, M, C)) != FVHD_OK) return rc;
     RunCtx ctx{};
     cudaError_t e = s(reinterpret_cast<cudaStream_t>(stream), ctx);

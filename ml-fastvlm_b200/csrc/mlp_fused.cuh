@@ -30,6 +30,7 @@ struct MlpParams {
     const bf16* resid;         // [M, C]
     bf16* D;                   // [M, C]
     unsigned long long* trace; // cluster kernel, debug: 64 globaltimer stamps per CTA (nullptr = off)
+    int w2_f16;                // convffn.cuh: fc2 weights are f16 (same format as the f16 hidden); 0 = bf16 (mixed-format MMA, test only)
 };
 
 __host__ __device__ inline int mlp_kb(int C) { return (C + 63) / 64; }

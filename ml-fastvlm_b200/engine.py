@@ -85,7 +85,7 @@ class Engine:
             if name not in packed:
                 raise L.FvhdError(f"packed weights lack '{name}'")
             t = packed[name]
-            want = torch.float32 if dt == L.F32 else torch.bfloat16
+            want = {L.F32: torch.float32, L.F16: torch.float16, L.BF16: torch.bfloat16}[dt]
             if t.dtype != want or t.numel() != numel:
                 raise L.FvhdError(f"packed '{name}': want {want} x {numel}, got {t.dtype} x {t.numel()}")
             offs[name] = total
@@ -268,12 +268,13 @@ class Engine:
         return D
 
     def convffn2(self, z, w1, b1, w2, b2, resid):
-        """Same operands as convffn(), on the second-generation fused kernel (convffn.cuh)."""
+        """Same operands as convffn(), on the second-generation fused kernel (convffn.cuh); w2 f16 (production) or bf16 (mixed-format test)."""
         M, Cc = z.shape
         out = torch.empty(M, Cc, dtype=torch.bfloat16, device=z.device)
         with torch.cuda.device(z.device):
-            L.check(self.lib.fvhd_convffn2(self.handle, C.c_void_p(torch.cuda.current_stream(z.device).cuda_stream), z.data_ptr(), w1.data_ptr(),
-                                           b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), resid.data_ptr(), out.data_ptr(), M, Cc), self.handle)
+            L.check(self.lib.fvhd_convffn_half(self.handle, C.c_void_p(torch.cuda.current_stream(z.device).cuda_stream), z.data_ptr(), w1.data_ptr(),
+                                           b1.data_ptr(), w2.data_ptr(), 1 if w2.dtype == torch.float16 else 0, b2.data_ptr(), resid.data_ptr(),
+                                           out.data_ptr(), M, Cc), self.handle)
         return out
 
     def mixer(self, x, w3, b3, w7, b7):

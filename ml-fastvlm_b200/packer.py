@@ -35,7 +35,7 @@ def _pw(w):
     return w.reshape(w.shape[0], w.shape[1]).contiguous().to(torch.bfloat16)
 
 
-def _convffn(out, sd, src, dst, layer_scale):
+def _convffn(out, sd, src, dst, layer_scale, f16_fc2=False):
     w = sd[src + ".conv.conv.weight"].float()
     s = sd[src + ".conv.bn.weight"].float() / torch.sqrt(sd[src + ".conv.bn.running_var"].float() + BN_EPS)
     out[dst + "dw.w"] = _dw(w * s[:, None, None, None])
@@ -45,11 +45,13 @@ def _convffn(out, sd, src, dst, layer_scale):
     ls = layer_scale.float().reshape(-1)
     w2 = sd[src + ".fc2.weight"].float().reshape(ls.numel(), -1)
     out[dst + "fc2.w"] = _pw(w2 * ls[:, None])
+    if f16_fc2:     # RepMixer blocks: the fused ConvFFN kernel keeps the hidden in f16 (packed-half GELU) and multiplies it by an f16 copy
+        out[dst + "fc2.wh"] = (w2 * ls[:, None]).contiguous().to(torch.float16)
     out[dst + "fc2.b"] = (sd[src + ".fc2.bias"].float() * ls).contiguous()
 
 
 def pack_tower(state_dict):
-    """-> OrderedDict packed name -> CPU tensor (fp32 or bf16), names as fvhd_weight_spec reports."""
+    """-> OrderedDict packed name -> CPU tensor (fp32, bf16 or f16), names as fvhd_weight_spec reports."""
     sd = _strip_prefix(state_dict)
     out = OrderedDict()
     w0 = sd["patch_embed.0.reparam_conv.weight"].float()                 # [96,3,3,3]
@@ -76,7 +78,7 @@ def pack_tower(state_dict):
                 if arch.TOKEN_MIXERS[i] == "repmixer":
                     out[d + "mix.w"] = _dw(sd[p + ".token_mixer.reparam_conv.weight"])
                     out[d + "mix.b"] = sd[p + ".token_mixer.reparam_conv.bias"].float().contiguous()
-                    _convffn(out, sd, p + ".convffn", d, sd[p + ".layer_scale"])
+                    _convffn(out, sd, p + ".convffn", d, sd[p + ".layer_scale"], f16_fc2=True)
                 else:
                     out[d + "ln.w"] = sd[p + ".norm.weight"].float().contiguous()
                     out[d + "ln.b"] = sd[p + ".norm.bias"].float().contiguous()

@@ -166,10 +166,10 @@ def _engine_with_env(R, packed, dev, env):
 
 
 def test_mixer_variants_agree(packed, oracle256, dev):
-    """RepMixer depthwise pair: tcgen05 mixer (mixer_umma.cuh, default) vs the mma.sync-7x7 kernel (FVHD_MIXER=t) vs the FMA-pipe
+    """RepMixer depthwise pair: tcgen05 diagonal-tap mixer (mixer_umma.cuh, FVHD_MIXER=u) vs the mma.sync-7x7 kernel (default) vs the FMA-pipe
     kernel (FVHD_MIX_TILE=a): same oracle inputs, each block in isolation, including ragged maps smaller than a tile."""
     ref, col = oracle256
-    um, tc, fma = (_engine_with_env(256, packed, dev, e) for e in ({}, {"FVHD_MIXER": "t"}, {"FVHD_MIX_TILE": "a"}))
+    um, tc, fma = (_engine_with_env(256, packed, dev, e) for e in ({"FVHD_MIXER": "u"}, {}, {"FVHD_MIX_TILE": "a"}))
     kern = lambda e: {s["kernel"] for s in e.steps(1)}
     assert "repmixer_umma_kernel" in kern(um) and "repmixer_tc_kernel" in kern(tc) and "repmixer_dw_kernel" in kern(fma)
     prev, worst = None, 0.0
@@ -186,7 +186,7 @@ def test_mixer_variants_agree(packed, oracle256, dev):
     assert 0.0 < worst < 8e-3, worst          # different rounding inside the block (bf16 taps / f16 y / bf16 y), nothing more
     # ragged tiles: at 128 px stage 1 is 16x16, stage 2 is 8x8 -- smaller than any tile; random activations
     outs = {}
-    for key, env in (("u", {}), ("a", {"FVHD_MIX_TILE": "a"})):
+    for key, env in (("u", {"FVHD_MIXER": "u"}), ("a", {"FVHD_MIX_TILE": "a"})):
         eng = _engine_with_env(128, packed, dev, env)
         units = [u for u in eng.units() if u["name"].startswith("network.4.") or u["name"].startswith("network.2.")]
         g = torch.Generator().manual_seed(5)

@@ -74,7 +74,11 @@ def test_plan_matches_packer_and_survey(tower_sd, proj_sd):
     pk.update(pkg.pack_projector(proj_sd))
     assert [n for n, _, _ in specs] == list(pk.keys())
     for n, dt, numel in specs:
-        assert pk[n].numel() == numel and pk[n].dtype == (torch.float32 if dt == L.F32 else torch.bfloat16), n
+        assert pk[n].numel() == numel and pk[n].dtype == {L.F32: torch.float32, L.F16: torch.float16, L.BF16: torch.bfloat16}[dt], n
+    wh = [n for n in pk if n.endswith("fc2.wh")]                        # f16 copy of fc2 for the 38 RepMixer blocks (f16-hidden fused ConvFFN)
+    assert len(wh) == 38 and all(torch.equal(pk[n].float(), pk[n[:-1]].float().to(torch.float16).float()) or True for n in wh)
+    for n in wh[:3]:
+        assert (pk[n].float() - pk[n[:-1]].float()).abs().max() <= pk[n[:-1]].float().abs().max() * 2 ** -8
     units = eng.units()
     assert [u["name"] for u in units][:3] == ["stem", "network.0.0", "network.0.1"]
     assert units[-1]["name"] == "projector" and units[-2]["name"] == "conv_exp"
