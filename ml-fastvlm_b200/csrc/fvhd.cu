@@ -23,6 +23,7 @@
 #include "stem_attn_se.cuh"
 #include "mixer_tc.cuh"
 #include "mixer_umma.cuh"
+#include "mixer_tc2.cuh"
 #include "convffn.cuh"
 
 using namespace fvhd;
@@ -272,9 +273,9 @@ int g_gemm_max_cs = 1;        // FVHD_GEMM_CS=1|2|4 caps the GEMM cluster size. 
                               // the limit and multicast only reduces L2 reads -- measured no gain (profiles/r01_f_summary.md)
 bool g_use_cluster_mlp = true; // FVHD_NO_CLUSTER_MLP=1: stage-2 (C = 384) ConvFFN as two GEMM launches instead of the 4-CTA-cluster kernel
 bool g_use_fused_mlp = true;  // FVHD_NO_FUSED_MLP=1: ConvFFN as two GEMM launches (reference path of the bit-exactness test)
-const int g_convffn_default = 1;
-int g_convffn_gen = 1;         // FVHD_CONVFFN=2: second-generation fused ConvFFN kernel (convffn.cuh); 1: mlp_fused / two GEMMs
-char g_mixer_mode = 't';       // FVHD_MIXER=t: mma.sync 7x7 (mixer_tc.cuh, default); u: tcgen05 diagonal-tap mixer (mixer_umma.cuh: correct, but
+const int g_convffn_default = 2;
+int g_convffn_gen = 1;         // FVHD_CONVFFN=2 (default): second-generation fused ConvFFN kernel (convffn.cuh); 1: mlp_fused (C <= 192) / two GEMMs
+char g_mixer_mode = 't';       // FVHD_MIXER=t: mma.sync 7x7 (mixer_tc.cuh, default); 2: both convs on mma.sync, 16 ch per CTA (mixer_tc2.cuh); u: tcgen05 diagonal-tap mixer (mixer_umma.cuh: correct, but
                                // smem-A-read bound -- 602 vs 434 us/img at batch 32, profiles/r02_*); f: FMA pipes (dwconv.cuh)
 unsigned long long* g_gemm_trace = nullptr;   // fvhd_debug_gemm_trace: device buffer, 16 stamps per CTA
 int g_force_bn = 0;                            // fvhd_debug_gemm_trace: force the N tile (0 = cost model)
@@ -352,6 +353,7 @@ int ensure_cuda(fvhd_handle h) {
     CUDA_TRY(h, set_smem(repmixer_dw_kernel<16, 16, 512, 6, 4, 2>, MixCfgT<16, 16>::SMEM));
     CUDA_TRY(h, set_smem(repmixer_tc_kernel, MixTc::SMEM));
     CUDA_TRY(h, set_smem(repmixer_umma_kernel, MixU::SMEM));
+    CUDA_TRY(h, set_smem(repmixer_tc2_kernel, MixT2::SMEM));
     { const char* e = getenv("FVHD_MIXER"); g_mixer_mode = (e && e[0]) ? e[0] : 't'; }
     { const char* e = getenv("FVHD_CONVFFN"); g_convffn_gen = (e && e[0] == '2') ? 2 : (e && e[0] == '1') ? 1 : g_convffn_default; }
     CUDA_TRY(h, set_smem(convffn_tcgen05_kernel<96>, CfCfg<96>::SMEM));
@@ -384,12 +386,12 @@ int make_tmap(fvhd_handle h, CUtensorMap* m, const void* ptr, int64_t rows, int6
 }
 
 // NHWC bf16 activation [B, H, W, C] -> 4-D tensor map, box {32 channels, box_w, box_h, 1}, no swizzle, zero OOB fill.
-int make_tmap_nhwc(fvhd_handle h, CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int box_w, int box_h) {
+int make_tmap_nhwc(fvhd_handle h, CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int box_w, int box_h, int box_c = DW_CG) {
     if ((uintptr_t)ptr & 15) return fail(h, FVHD_ERR_INVALID, "TMA operand must be 16-B aligned (ptr %p)", ptr);
     if (box_w > 256 || box_h > 256) return fail(h, FVHD_ERR_INVALID, "TMA box %dx%d too large", box_w, box_h);
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)DW_CG, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -701,7 +703,17 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
             // default: 16x16 tiles with the 7x7 on the tensor cores (mixer_tc.cuh).  FVHD_MIX_TILE selects the FMA-pipe variants
             // of dwconv.cuh instead: 'a' = their old automatic choice, '1' = 16x16/256 thr, '8' = 8x16/128 thr, '5' = 16x16/512 thr.
             const long ctas16 = (long)((W + 15) / 16) * ((H + 15) / 16) * (c / DW_CG) * batch;
-            if (g_mixer_mode == 'u' && !getenv("FVHD_MIX_TILE")) {
+            if (g_mixer_mode == '2' && !getenv("FVHD_MIX_TILE") && c % MixT2::CG == 0) {
+                // both convs on mma.sync, 16 channels per CTA (mixer_tc2.cuh)
+                const int tx2 = (W + MixT2::TOW - 1) / MixT2::TOW, ty2 = (H + MixT2::TOH - 1) / MixT2::TOH;
+                const dim3 grid2(tx2 * ty2, c / MixT2::CG, batch);
+                CUtensorMap tm2;
+                if ((rc = make_tmap_nhwc(h, &tm2, in, batch, H, W, c, MixT2::XP, MixT2::XH, MixT2::CG)) != FVHD_OK) return rc;
+                bf16 *y2 = bf.Y, *z2 = bf.Z;
+                pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+                    return launch_k(repmixer_tc2_kernel, grid2, dim3(MixT2::NT), MixT2::SMEM, s, tm2, y2, z2, w3, b3, w7, b7, H, W, c, tx2);
+                }, "repmixer_tc2_kernel", U, 2.0 * Md * c * 58, 3.0 * Md * c * 2);
+            } else if (g_mixer_mode == 'u' && !getenv("FVHD_MIX_TILE")) {
                 Step ms;
                 if ((rc = make_mixer_umma_step(h, &ms, in, bf.Y, bf.Z, w3, b3, w7, b7, batch, H, W, c)) != FVHD_OK) return rc;
                 pl.add(ms, "repmixer_umma_kernel", U, 2.0 * Md * c * 58, 3.0 * Md * c * 2);
@@ -1425,7 +1437,18 @@ int fvhd_mixer(fvhd_handle h, void* stream, const void* x, const void* w3, const
     if (rc != FVHD_OK) return rc;
     if (!x || !w3 || !b3 || !w7 || !b7 || !y || !z || batch < 1 || H < 1 || W < 1) return fail(h, FVHD_ERR_INVALID, "fvhd_mixer: null operand or empty shape");
     Step s;
-    if ((rc = make_mixer_umma_step(h, &s, (const bf16*)x, (bf16*)y, (bf16*)z, (const float*)w3, (const float*)b3, (const float*)w7,
+    if (g_mixer_mode == '2') {      // FVHD_MIXER=2: the mma.sync kernel of mixer_tc2.cuh; otherwise the tcgen05 diagonal-tap kernel
+        if (C % MixT2::CG) return fail(h, FVHD_ERR_INVALID, "fvhd_mixer: C %% 16 != 0");
+        const int tx2 = (W + MixT2::TOW - 1) / MixT2::TOW, ty2 = (H + MixT2::TOH - 1) / MixT2::TOH;
+        const dim3 grid2(tx2 * ty2, C / MixT2::CG, batch);
+        CUtensorMap tm2;
+        if ((rc = make_tmap_nhwc(h, &tm2, x, batch, H, W, C, MixT2::XP, MixT2::XH, MixT2::CG)) != FVHD_OK) return rc;
+        bf16 *y2 = (bf16*)y, *z2 = (bf16*)z;
+        const float *w3f = (const float*)w3, *b3f = (const float*)b3, *w7f = (const float*)w7, *b7f = (const float*)b7;
+        s = [=](cudaStream_t st, const RunCtx&) -> cudaError_t {
+            return launch_k(repmixer_tc2_kernel, grid2, dim3(MixT2::NT), MixT2::SMEM, st, tm2, y2, z2, w3f, b3f, w7f, b7f, H, W, C, tx2);
+        };
+    } else if ((rc = make_mixer_umma_step(h, &s, (const bf16*)x, (bf16*)y, (bf16*)z, (const float*)w3, (const float*)b3, (const float*)w7,
                                    (const float*)b7, batch, H, W, C)) != FVHD_OK) return rc;
     RunCtx ctx{};
     cudaError_t e = s(reinterpret_cast<cudaStream_t>(stream), ctx);

@@ -299,7 +299,7 @@ def test_fused_convffn_is_bit_identical_to_two_gemms(packed, dev):
     outs = []
     for env_val in ("0", "1"):
         f = tempfile.NamedTemporaryFile(suffix=".pt", delete=False).name
-        env = dict(os.environ, FVHD_NO_FUSED_MLP=env_val, FVHD_NO_CLUSTER_MLP="1")
+        env = dict(os.environ, FVHD_NO_FUSED_MLP=env_val, FVHD_NO_CLUSTER_MLP="1", FVHD_CONVFFN="1")     # first-generation fused kernel
         subprocess.run([sys.executable, "-c", code, f], check=True, env=env, timeout=300)
         outs.append(torch.load(f))
         os.unlink(f)
@@ -312,13 +312,23 @@ def test_fused_convffn_is_bit_identical_to_two_gemms(packed, dev):
     # the reference's own bf16 run sits 3.8e-2 from its fp32 run).  Bound: two valid bf16 pipelines must agree to that
     # level; parity of the cluster path itself is checked unit by unit and end to end against the oracle above.
     f = tempfile.NamedTemporaryFile(suffix=".pt", delete=False).name
-    subprocess.run([sys.executable, "-c", code, f], check=True, env=dict(os.environ, FVHD_NO_FUSED_MLP="0", FVHD_NO_CLUSTER_MLP="0"), timeout=300)
+    subprocess.run([sys.executable, "-c", code, f], check=True, env=dict(os.environ, FVHD_NO_FUSED_MLP="0", FVHD_NO_CLUSTER_MLP="0", FVHD_CONVFFN="1"), timeout=300)
     clus = torch.load(f)
     os.unlink(f)
     assert clus["launches"] == outs[0]["launches"] - 24               # 24 stage-2 blocks lose one launch each
     assert torch.isfinite(clus["p"].float()).all()
     dt, dp = rel_l2(clus["t"], outs[0]["t"]), rel_l2(clus["p"], outs[0]["p"])
     assert dt < 4e-2 and dp < 4e-2, (dt, dp)
+    # the default plan (second-generation fused kernel, f16 hidden + packed-half GELU, convffn.cuh): same launch count as the
+    # fully fused first-generation plan, and -- a different but equally valid rounding of the hidden -- within the same bound
+    f = tempfile.NamedTemporaryFile(suffix=".pt", delete=False).name
+    env = {k: v for k, v in os.environ.items() if k not in ("FVHD_CONVFFN", "FVHD_NO_FUSED_MLP", "FVHD_NO_CLUSTER_MLP")}
+    subprocess.run([sys.executable, "-c", code, f], check=True, env=env, timeout=300)
+    gen2 = torch.load(f)
+    os.unlink(f)
+    assert gen2["launches"] == clus["launches"]
+    dt, dp = rel_l2(gen2["t"], outs[1]["t"]), rel_l2(gen2["p"], outs[1]["p"])
+    assert torch.isfinite(gen2["p"].float()).all() and dt < 4e-2 and dp < 4e-2, (dt, dp)
 
 
 @pytest.mark.parametrize("C,M", [(96, 128 * 150 + 40), (192, 128 * 9), (384, 4096), (384, 128 * 80 + 128)])

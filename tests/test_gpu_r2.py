@@ -235,8 +235,15 @@ def _mixer_ref(x_nhwc, w3, b3, w7, b7, round_weights):
     (3, 40, 24, 32),       # ragged in both directions, 2 channel groups, batch 3
     (1, 96, 96, 48),       # 1536-px geometry (3 tiles across), 3 groups
 ])
-def test_umma_mixer_vs_torch(dev, B, H, W, C):
-    eng = pkg.Engine(64, 0, 2, 1)
+@pytest.mark.parametrize("mode", ["u", "2"])
+def test_umma_mixer_vs_torch(dev, B, H, W, C, mode):
+    """mode u: tcgen05 diagonal-tap kernel (mixer_umma.cuh, bf16 taps); mode 2: both convs on mma.sync (mixer_tc2.cuh, f16 taps)."""
+    os.environ["FVHD_MIXER"] = mode                      # read when a handle first touches CUDA
+    try:
+        eng = pkg.Engine(64, 0, 2, 1)
+        eng.gemm(torch.zeros(8, 64, dtype=torch.bfloat16, device=dev), torch.zeros(8, 64, dtype=torch.bfloat16, device=dev))
+    finally:
+        os.environ.pop("FVHD_MIXER", None)
     g = torch.Generator().manual_seed(B * 1000 + H * 10 + C)
     x = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16)
     w3 = torch.randn(9, C, generator=g) / 3.0
@@ -245,18 +252,24 @@ def test_umma_mixer_vs_torch(dev, B, H, W, C):
     b7 = torch.randn(C, generator=g) * 0.1
     y, z = eng.mixer(x.to(dev), w3.to(dev), b3.to(dev), w7.to(dev), b7.to(dev))
     torch.cuda.synchronize()
-    yr, zr = _mixer_ref(x, w3, b3, w7, b7, round_weights=True)       # the kernel's own arithmetic: bf16 taps, fp32 accumulate
+    yr, zr = _mixer_ref(x, w3, b3, w7, b7, round_weights=(mode == "u"))   # mode u rounds the taps to bf16; mode 2 to f16 (~exact)
     ye, ze = _mixer_ref(x, w3, b3, w7, b7, round_weights=False)      # exact fp32 taps (what the oracle computes)
     ey, ez = rel_l2(y.float(), yr), rel_l2(z.float(), zr)
-    print(f"umma mixer {B}x{H}x{W}x{C}: y {ey:.2e} z {ez:.2e} | vs fp32 taps: y {rel_l2(y.float(), ye):.2e} z {rel_l2(z.float(), ze):.2e}")
+    print(f"mixer[{mode}] {B}x{H}x{W}x{C}: y {ey:.2e} z {ez:.2e} | vs fp32 taps: y {rel_l2(y.float(), ye):.2e} z {rel_l2(z.float(), ze):.2e}")
     assert torch.isfinite(y.float()).all() and torch.isfinite(z.float()).all()
     assert ey < 3e-3 and ez < 4e-3, (ey, ez)                           # bf16 output rounding (y also feeds z)
     assert rel_l2(y.float(), ye) < 5e-3 and rel_l2(z.float(), ze) < 6e-3
 
 
-def test_umma_mixer_identity_taps(dev):
+@pytest.mark.parametrize("mode", ["u", "2"])
+def test_umma_mixer_identity_taps(dev, mode):
     """Centre taps = 1, everything else 0: y == x + b3, z == y + b7 exactly (bf16 in, fp32 accumulate, bf16 out)."""
-    eng = pkg.Engine(64, 0, 2, 1)
+    os.environ["FVHD_MIXER"] = mode
+    try:
+        eng = pkg.Engine(64, 0, 2, 1)
+        eng.gemm(torch.zeros(8, 64, dtype=torch.bfloat16, device=dev), torch.zeros(8, 64, dtype=torch.bfloat16, device=dev))
+    finally:
+        os.environ.pop("FVHD_MIXER", None)
     g = torch.Generator().manual_seed(1)
     B, H, W, C = 1, 48, 80, 32
     x = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16)
