@@ -277,7 +277,12 @@ def test_umma_mixer_identity_taps(dev, mode):
     w7 = torch.zeros(49, C); w7[24] = 1.0
     zb = torch.zeros(C)
     y, z = eng.mixer(x.to(dev), w3.to(dev), zb.to(dev), w7.to(dev), zb.to(dev))
-    assert torch.equal(y.cpu(), x) and torch.equal(z.cpu(), x)
+    if mode == "u":
+        assert torch.equal(y.cpu(), x) and torch.equal(z.cpu(), x)
+    else:       # f16 planes: bf16 values below 2^-14 land on the f16 subnormal grid (quantum 2^-24); everything else is exact
+        assert (y.float().cpu() - x.float()).abs().max().item() <= 2 ** -24 and (z.float().cpu() - x.float()).abs().max().item() <= 2 ** -23
+        big = x.float().abs() >= 2 ** -14
+        assert torch.equal(y.cpu()[big], x[big])
 
 
 # ------------------------------------------------------------------ second-generation fused ConvFFN (convffn.cuh)
