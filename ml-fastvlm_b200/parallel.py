@@ -91,6 +91,10 @@ class GatheredEncoder:
             raise ValueError("at most 8 peers (one NVSwitch domain)")
         n, h = engine.num_tokens, engine.hidden
         self.buf = symm_mem.empty((self.batch, n, h), dtype=torch.bfloat16, device=engine.device)
+        try:        # older torch needs the group enabled explicitly; newer versions do it inside rendezvous
+            symm_mem.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:  # noqa: BLE001
+            pass
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         self.slots = gather_slots(self.batch, self.world)
         a, nb = self.slots[self.rank]
