@@ -175,6 +175,10 @@ int fvhd_debug_mixer_trace(void* dev_buf_8_u64_per_cta);
 int fvhd_gemm(fvhd_handle h, void* stream, const void* A, const void* W, const void* bias, const void* residual,
               void* D, int M, int N, int K, int act);
 
+/* Test entry: the MHSA core softmax((q 32^-1/2) k^T) v of one attention block (mci.py:675-679) on qkv = [B*N, 3C] bf16 (q | k | v,
+ * heads of 32) -> out [B*N, C] bf16; kernel per FVHD_ATTN (u: tcgen05/TMEM, attention_umma.cuh; default: mma.sync). */
+int fvhd_attention(fvhd_handle h, void* stream, const void* qkv, void* out, int batch, int N, int C);
+
 /* Test entry: the second-generation fused ConvFFN kernel (convffn.cuh; one CTA per 128-row tile, packed-half GELU, f16 hidden),
  * same operands as fvhd_convffn except w2: f16 [C, 4C] when w2_is_f16 (the production format, packer `fc2.wh`), else bf16;
  * C in {96, 192, 384}, any M. */

@@ -25,6 +25,7 @@
 #include "mixer_umma.cuh"
 #include "mixer_tc2.cuh"
 #include "convffn.cuh"
+#include "attention_umma.cuh"
 
 using namespace fvhd;
 
@@ -99,6 +100,8 @@ struct fvhd_handle_s {
     uint8_t* rs_src = nullptr; size_t rs_src_bytes = 0;
     float* rs_lut = nullptr;
     size_t stage_in_bytes = 0, stage_out_bytes = 0;
+    float* splitk_ws = nullptr;     // split-K partial tiles (GEMM_SPLITK_WS_BYTES) + per-tile arrival counters, owned by the handle
+    int* splitk_cnt = nullptr;
 };
 
 namespace {
@@ -268,12 +271,17 @@ Buffers carve(fvhd_handle h, int batch) {
 // ------------------------------------------------------------------ launches
 // All kernels go through cudaLaunchKernelEx with programmatic stream serialization (PDL): a kernel may begin its
 // prologue while the previous one drains; the kernels themselves order their global accesses with pdl_wait().
+bool g_use_splitk = true;      // FVHD_NO_SPLITK=1: small-M GEMMs run one CTA per output tile (no k-slices)
+const size_t kSplitKWsBytes = 32u << 20;
+const int kSplitKTiles = 4096;
 bool g_use_pdl = true;
 int g_gemm_max_cs = 1;        // FVHD_GEMM_CS=1|2|4 caps the GEMM cluster size.  Default 1: at batch 1 the delivered-bytes rate is
                               // the limit and multicast only reduces L2 reads -- measured no gain (profiles/r01_f_summary.md)
 bool g_use_cluster_mlp = true; // FVHD_NO_CLUSTER_MLP=1: stage-2 (C = 384) ConvFFN as two GEMM launches instead of the 4-CTA-cluster kernel
 bool g_use_fused_mlp = true;  // FVHD_NO_FUSED_MLP=1: ConvFFN as two GEMM launches (reference path of the bit-exactness test)
 const int g_convffn_default = 2;
+const char g_attn_default = 'm';
+char g_attn_mode = 'm';        // FVHD_ATTN=u: tcgen05 / TMEM attention core (attention_umma.cuh); m: mma.sync kernel (stem_attn_se.cuh)
 int g_convffn_gen = 1;         // FVHD_CONVFFN=2 (default): second-generation fused ConvFFN kernel (convffn.cuh); 1: mlp_fused (C <= 192) / two GEMMs
 char g_mixer_mode = 't';       // FVHD_MIXER=t: mma.sync 7x7 (mixer_tc.cuh, default); 2: both convs on mma.sync, 16 ch per CTA (mixer_tc2.cuh); u: tcgen05 diagonal-tap mixer (mixer_umma.cuh: correct, but
                                // smem-A-read bound -- 602 vs 434 us/img at batch 32, profiles/r02_*); f: FMA pipes (dwconv.cuh)
@@ -355,6 +363,8 @@ int ensure_cuda(fvhd_handle h) {
     CUDA_TRY(h, set_smem(repmixer_umma_kernel, MixU::SMEM));
     CUDA_TRY(h, set_smem(repmixer_tc2_kernel, MixT2::SMEM));
     { const char* e = getenv("FVHD_MIXER"); g_mixer_mode = (e && e[0]) ? e[0] : 't'; }
+    { const char* e = getenv("FVHD_ATTN"); g_attn_mode = (e && e[0]) ? e[0] : g_attn_default; }
+    CUDA_TRY(h, set_smem(attention_umma_kernel, AttU::SMEM));
     { const char* e = getenv("FVHD_CONVFFN"); g_convffn_gen = (e && e[0] == '2') ? 2 : (e && e[0] == '1') ? 1 : g_convffn_default; }
     CUDA_TRY(h, set_smem(convffn_tcgen05_kernel<96>, CfCfg<96>::SMEM));
     CUDA_TRY(h, set_smem(convffn_tcgen05_kernel<192>, CfCfg<192>::SMEM));
@@ -366,19 +376,24 @@ int ensure_cuda(fvhd_handle h) {
     CUDA_TRY(h, set_smem(stem_kernel<__half>, STEM_SMEM));
     CUDA_TRY(h, set_smem(stem_kernel<bf16>, STEM_SMEM));
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    { const char* e = getenv("FVHD_NO_SPLITK"); g_use_splitk = !(e && e[0] == '1'); }
+    CUDA_TRY(h, cudaMalloc(&h->splitk_ws, kSplitKWsBytes));
+    CUDA_TRY(h, cudaMalloc(&h->splitk_cnt, kSplitKTiles * sizeof(int)));
+    CUDA_TRY(h, cudaMemset(h->splitk_cnt, 0, kSplitKTiles * sizeof(int)));
     h->cuda_ready = true;
     return FVHD_OK;
 }
 
 // bf16 row-major [rows, K] matrix with row pitch `ld` elements -> 2-D tensor map, box {64, box_rows}, 128-B swizzle.
-int make_tmap(fvhd_handle h, CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows, int box_cols = GEMM_BK) {
+int make_tmap(fvhd_handle h, CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows, int box_cols = GEMM_BK,
+              CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     if (((uintptr_t)ptr & 15) || (ld * 2) % 16) return fail(h, FVHD_ERR_INVALID, "TMA operand must be 16-B aligned (ptr %p, ld %lld)", ptr, (long long)ld);
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, FVHD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld ld=%lld box=%d", (int)r,
                                        (long long)rows, (long long)K, (long long)ld, box_rows);
@@ -492,6 +507,19 @@ int make_gemm_step(fvhd_handle h, Step* out, const IoBlock* io, int rows_per_ima
     p.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
     p.tiles_n = (N + p.BN - 1) / p.BN;
     p.ctiles = p.share_b ? ((p.tiles_m + p.cs - 1) / p.cs) * p.tiles_n : p.tiles_m * ((p.tiles_n + p.cs - 1) / p.cs);
+    p.split_k = 1; p.kb_per_split = num_kb; p.ws = nullptr; p.counters = nullptr;
+    if (g_use_splitk && p.cs == 1 && h->splitk_ws && 2 * p.ctiles <= h->num_sms && num_kb >= 8 && p.ctiles <= kSplitKTiles) {
+        // weight-streaming regime (few output tiles, long K): slice K so that ~all SMs stream weights; >= 4 k-blocks per slice
+        int S = h->num_sms / p.ctiles;
+        if (S > num_kb / 4) S = num_kb / 4;
+        while (S > 1 && (size_t)p.ctiles * S * GEMM_BM * p.BN * sizeof(float) > kSplitKWsBytes) --S;
+        if (S > 1) {
+            const int kbs = (num_kb + S - 1) / S;
+            S = (num_kb + kbs - 1) / kbs;
+            p.split_k = S; p.kb_per_split = kbs; p.ws = h->splitk_ws; p.counters = h->splitk_cnt;
+            p.ctiles *= S;                      // work items = (tile, k-slice)
+        }
+    }
     p.trace = g_gemm_trace;
     p.D = D; p.io = io; p.rows_per_image = rows_per_image > 0 ? rows_per_image : 1; p.ldd = ldd; p.bias = bias; p.residual = residual; p.ldr = ldr; p.act = act;
     CUtensorMap ta, tb, td;
@@ -594,6 +622,20 @@ int add_fused_mlp_step(fvhd_handle h, Plan& pl, int unit, const std::string& p, 
     int rc = make_fused_mlp_step(h, &st, z, WB(h, p + "fc1.w"), WF(h, p + "fc1.b"), WB(h, p + "fc2.w"), WF(h, p + "fc2.b"), resid, out, M, c);
     if (rc != FVHD_OK) return rc;
     pl.add(st, "mlp_fused_tcgen05_kernel", unit, 2.0 * gemm_flops(M, 4 * c, c), 2.0 * (3.0 * M * c + 8.0 * c * c) + 20.0 * c);
+    return FVHD_OK;
+}
+
+// MHSA core on tcgen05 (attention_umma.cuh): one CTA per (256 queries, head, image).
+int make_attention_umma_step(fvhd_handle h, Step* st, const bf16* qkv, bf16* out, int batch, int N, int c, float scale_log2e) {
+    AttUParams ap{};
+    ap.out = out; ap.N = N; ap.C = c; ap.qpairs = (N + 2 * AttU::QT - 1) / (2 * AttU::QT); ap.scale_log2e = scale_log2e;
+    CUtensorMap tm;
+    int rc = make_tmap(h, &tm, qkv, (int64_t)batch * N, 3LL * c, 3LL * c, AttU::KT, AttU::HD, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc != FVHD_OK) return rc;
+    const dim3 grid((unsigned)ap.qpairs, (unsigned)(c / AttU::HD), (unsigned)batch);
+    *st = [=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+        return launch_k(attention_umma_kernel, grid, dim3(AttU::THREADS), AttU::SMEM, s, tm, ap);
+    };
     return FVHD_OK;
 }
 
@@ -775,11 +817,17 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
                 return launch_k(layernorm_channel_kernel<6>, dim3(lngrid), dim3(256), 0, s, in, t1, lw, lb, M, 1e-5f);
             }, "layernorm_channel_kernel", U, 0.0, 4.0 * Md * c);
             if ((rc = add_gemm(h, pl, U, t1, c, WB(h, p + "qkv.w"), nullptr, nullptr, 0, qkv, 3 * c, M, 3 * c, c, 0)) != FVHD_OK) return rc;
-            const dim3 agrid((N + 63) / 64, c / 32, batch);
             const float sl2 = 0.17677669529663687f * 1.4426950408889634f;   // 32^-0.5 * log2(e)
-            pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
-                return launch_k(attention_kernel, agrid, dim3(128), 0, s, qkv, t1, N, c, sl2);
-            }, "attention_kernel", U, 4.0 * batch * (double)N * N * c, 8.0 * Md * c);
+            if (g_attn_mode == 'u') {       // tcgen05 / TMEM flash attention (attention_umma.cuh)
+                Step as;
+                if ((rc = make_attention_umma_step(h, &as, qkv, t1, batch, N, c, sl2)) != FVHD_OK) return rc;
+                pl.add(as, "attention_umma_kernel", U, 4.0 * batch * (double)N * N * c, 8.0 * Md * c);
+            } else {
+                const dim3 agrid((N + 63) / 64, c / 32, batch);
+                pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+                    return launch_k(attention_kernel, agrid, dim3(128), 0, s, qkv, t1, N, c, sl2);
+                }, "attention_kernel", U, 4.0 * batch * (double)N * N * c, 8.0 * Md * c);
+            }
             if ((rc = add_gemm(h, pl, U, t1, c, WB(h, p + "proj.w"), WF(h, p + "proj.b"), in, c, x1, c, M, c, c, 0)) != FVHD_OK) return rc;
             { Step ds; if ((rc = make_dw_step<7, 1, 1, 0, 16, 16, 8>(h, &ds, x1, bf.Z, WF(h, p + "dw.w"), WF(h, p + "dw.b"), batch, H, W, c)) != FVHD_OK) return rc; pl.add(ds, "dwconv_kernel<7,1,1>", U, 2.0 * Md * c * 49, 4.0 * Md * c); }
             if ((rc = add_convffn_steps(h, pl, U, p, bf, bf.Z, x1, out, M, c)) != FVHD_OK) return rc;
@@ -945,6 +993,8 @@ int fvhd_destroy(fvhd_handle h) {
     if (h) {
         destroy_plans(h);
         if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+        if (h->splitk_ws) cudaFree(h->splitk_ws);
+        if (h->splitk_cnt) cudaFree(h->splitk_cnt);
         if (h->stage_in) cudaFree(h->stage_in);
         if (h->stage_out) cudaFree(h->stage_out);
         for (auto& kv : h->rs_tables) { cudaFree(kv.second.bounds); cudaFree(kv.second.kk); }
@@ -1427,6 +1477,26 @@ int fvhd_convffn_half(fvhd_handle h, void* stream, const void* z, const void* w1
     RunCtx ctx{};
     cudaError_t e = s(reinterpret_cast<cudaStream_t>(stream), ctx);
     if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "convffn2 launch failed: %s", cudaGetErrorString(e));
+    return FVHD_OK;
+}
+
+int fvhd_attention(fvhd_handle h, void* stream, const void* qkv, void* out, int batch, int N, int C) {
+    if (!h) return FVHD_ERR_INVALID;
+    int rc = ensure_cuda(h);
+    if (rc != FVHD_OK) return rc;
+    if (!qkv || !out || batch < 1 || N < 1 || C < 32 || C % 32) return fail(h, FVHD_ERR_INVALID, "fvhd_attention: bad arguments");
+    const float sl2 = 0.17677669529663687f * 1.4426950408889634f;
+    Step s;
+    if (g_attn_mode == 'u') {
+        if ((rc = make_attention_umma_step(h, &s, (const bf16*)qkv, (bf16*)out, batch, N, C, sl2)) != FVHD_OK) return rc;
+    } else {
+        const dim3 agrid((N + 63) / 64, C / 32, batch);
+        const bf16* q_ = (const bf16*)qkv; bf16* o_ = (bf16*)out;
+        s = [=](cudaStream_t st, const RunCtx&) -> cudaError_t { return launch_k(attention_kernel, agrid, dim3(128), 0, st, q_, o_, N, C, sl2); };
+    }
+    RunCtx ctx{};
+    cudaError_t e = s(reinterpret_cast<cudaStream_t>(stream), ctx);
+    if (e != cudaSuccess) return fail(h, FVHD_ERR_CUDA, "attention launch failed: %s", cudaGetErrorString(e));
     return FVHD_OK;
 }
 

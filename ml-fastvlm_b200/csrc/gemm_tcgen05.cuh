@@ -51,6 +51,14 @@ struct GemmParams {
     int ctiles;              // cluster-tiles = work items of one cluster
     unsigned long long* trace;   // debug: 16 globaltimer stamps per CTA (nullptr = off)
     int tma_store;           // 1: tmD is valid (D is library memory) -> full 64-column groups leave through TMA
+    // Split-K (small-M, weight-streaming GEMMs of stages 3-4 / projector at small batch: a 2 x 12-tile grid cannot keep 148 SMs
+    // streaming weights).  Work item = (tile, k-slice): every CTA accumulates its slice, writes the fp32 partial tile to `ws`
+    // and bumps the tile's counter; the LAST CTA to arrive re-reads all `split_k` partials in slice order (deterministic) and
+    // runs the ordinary epilogue.  Counters are self-resetting.  cs must be 1.
+    int split_k;             // 1 = off
+    int kb_per_split;        // k-blocks per slice
+    float* ws;               // [tiles][split_k][128][BN] fp32
+    int* counters;           // [tiles], zero before the first launch
 };
 
 __host__ __device__ inline int gemm_acc_stride(int bn) {     // TMEM columns per accumulator buffer (power of 2)
@@ -117,6 +125,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     };
     const uint32_t acc_stride = gemm_acc_stride(BN);
     const uint32_t tmem_cols = 2 * acc_stride;
+    // split-K: work item ct = tile * S + slice; slice ks covers k-blocks [ks * kbs, min(.., num_kb))
+    const int S = p.split_k > 1 ? p.split_k : 1;
+    const int kbs = S > 1 ? p.kb_per_split : num_kb;
+    auto item_kb = [&](int ct, int& tile, int& kb0, int& kb1) {
+        tile = ct / S;
+        kb0 = (ct - tile * S) * kbs;
+        kb1 = kb0 + kbs < num_kb ? kb0 + kbs : num_kb;
+    };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -151,9 +167,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             int pre = 0;
             if (CS == 1) {
                 for (int ct = cid; ct < p.ctiles && pre < stages; ct += nclusters) {
-                    int m0, n0;
-                    tile_origin(ct, m0, n0);
-                    for (int kb = 0; kb < num_kb && pre < stages; ++kb, ++pre) {
+                    int m0, n0, tile, kb0, kb1;
+                    item_kb(ct, tile, kb0, kb1);
+                    tile_origin(tile, m0, n0);
+                    for (int kb = kb0; kb < kb1 && pre < stages; ++kb, ++pre) {
                         mbar_expect_tx(&full_bar[pre], GEMM_A_STAGE_BYTES + b_stage_bytes);
                         tma_load_2d(smemB + (size_t)pre * b_stage_bytes, &tmB, kb * GEMM_BK, n0, &full_bar[pre]);
                     }
@@ -163,9 +180,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             GEMM_TRACE(2);
             int it = 0;
             for (int ct = cid; ct < p.ctiles; ct += nclusters) {
-                int m0, n0;
-                tile_origin(ct, m0, n0);
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                int m0, n0, tile, kb0, kb1;
+                item_kb(ct, tile, kb0, kb1);
+                tile_origin(tile, m0, n0);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % stages;
                     const uint32_t ph = (uint32_t)(it / stages) & 1u;
                     uint8_t* sa = smemA + (size_t)s * GEMM_A_STAGE_BYTES;
@@ -202,7 +220,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 mbar_wait(&tempty_bar[a], aph ^ 1u);            // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t acc = tmem_base + (uint32_t)a * acc_stride;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                int tile_, kb0, kb1;
+                item_kb(ct, tile_, kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % stages;
                     const uint32_t ph = (uint32_t)(it / stages) & 1u;
                     mbar_wait(&full_bar[s], ph);
@@ -213,7 +233,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k) {
                         // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in (addr >> 4) units
-                        umma_bf16(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_bf16(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
                     }
                     if (CS == 1) umma_commit(&empty_bar[s]);          // slot reusable once these MMAs have read it
                     else umma_commit_mc(&empty_bar[s], mc_mask);      // ... told to every producer that writes into it
@@ -236,11 +256,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         bool store_pending = false;
         int tl = 0;
         pdl_wait();                                         // residual / io reads and every global write come after this
+        int* sflag = reinterpret_cast<int*>(tmem_slot + 2);   // split-K: "this CTA is the last slice of its tile"
         for (int ct = cid; ct < p.ctiles; ct += nclusters, ++tl) {
             const int a = tl & 1;
             const uint32_t aph = (uint32_t)(tl >> 1) & 1u;
-            int m0, n0;
-            tile_origin(ct, m0, n0);
+            int m0, n0, tile, kb0_, kb1_;
+            item_kb(ct, tile, kb0_, kb1_);
+            tile_origin(tile, m0, n0);
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < p.M;
             bf16* drow;
@@ -287,19 +309,64 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             if (warp == 2 && lane == 0 && tl == 0) GEMM_TRACE(8);    // first accumulator ready
             tc_fence_after();
             const uint32_t lane_addr = tmem_base + (uint32_t)a * acc_stride + ((uint32_t)(q * 32) << 16);
+            bool do_epi = true;
+            if (S > 1) {
+                // ---- split-K: publish this slice's fp32 partial, then find out whether this CTA is the last slice of the tile
+                float* wsp = p.ws + ((size_t)ct * GEMM_BM + (size_t)(q * 32 + lane)) * (size_t)BN;
+                for (int g = hh; g < ngroups; g += 2) {
+                    const int gcol = g * 64;
+                    const int gw = (BN - gcol) < 64 ? (BN - gcol) : 64;
+                    for (int c = 0; c * 32 < gw; ++c) {
+                        uint32_t r[32];
+                        tmem_ld32(lane_addr + (uint32_t)(gcol + c * 32), r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<uint4*>(wsp + gcol + c * 32 + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    }
+                }
+                __threadfence();
+                named_bar_sync(1, GEMM_EPI_WARPS * 32);
+                if (warp == 2 && lane == 0) {
+                    const int old = atomicAdd(p.counters + tile, 1);
+                    const int last = old == S - 1;
+                    if (last) p.counters[tile] = 0;             // self-resetting: every other slice has already arrived
+                    *sflag = last;
+                }
+                named_bar_sync(1, GEMM_EPI_WARPS * 32);
+                do_epi = *sflag != 0;
+                if (do_epi) __threadfence();
+            }
+            // accumulator chunk loader: TMEM (ordinary) or the sum of the tile's S partials in slice order (split-K, deterministic)
+            auto load_chunk = [&](int colofs, uint32_t (&dst)[32]) {
+                if (S == 1) { tmem_ld32(lane_addr + (uint32_t)colofs, dst); return; }
+                float accv[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) accv[j] = 0.f;
+                for (int sl = 0; sl < S; ++sl) {
+                    const float4* src = reinterpret_cast<const float4*>(p.ws + ((size_t)(tile * S + sl) * GEMM_BM + (size_t)(q * 32 + lane)) * (size_t)BN + colofs);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 v4 = __ldcg(src + j);
+                        accv[4 * j] += v4.x; accv[4 * j + 1] += v4.y; accv[4 * j + 2] += v4.z; accv[4 * j + 3] += v4.w;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) dst[j] = __float_as_uint(accv[j]);
+            };
             int gk = 0;
-            for (int g = hh; g < ngroups; g += 2, ++gk) {
+            for (int g = hh; do_epi && g < ngroups; g += 2, ++gk) {
                 const int gcol = g * 64;                         // first tile column of the group
                 const int gw = (BN - gcol) < 64 ? (BN - gcol) : 64;   // 64, or 32 for the tail group of BN = 32 / 96
                 const bool via_tma = p.tma_store && gw == 64;
                 const float* bgrp = bstage + (gk & 1) * 64;
                 uint32_t r[2][32];
-                tmem_ld32(lane_addr + (uint32_t)gcol, r[0]);
+                load_chunk(gcol, r[0]);
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     if (c * 32 >= gw) break;
                     tmem_ld_wait();
-                    if (c == 0 && gw == 64) tmem_ld32(lane_addr + (uint32_t)(gcol + 32), r[1]);   // next chunk in flight
+                    if (c == 0 && gw == 64) load_chunk(gcol + 32, r[1]);   // next chunk in flight
                     const int col0 = n0 + gcol + c * 32;
 #pragma unroll
                     for (int g8 = 0; g8 < 4; ++g8) {

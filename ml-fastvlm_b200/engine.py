@@ -277,6 +277,15 @@ class Engine:
                                            out.data_ptr(), M, Cc), self.handle)
         return out
 
+    def attention(self, qkv, batch, n_tokens):
+        """MHSA core on qkv [B*N, 3C] bf16 -> [B*N, C] bf16 (kernel per FVHD_ATTN at handle creation)."""
+        Cc = qkv.shape[1] // 3
+        out = torch.empty(qkv.shape[0], Cc, dtype=torch.bfloat16, device=qkv.device)
+        with torch.cuda.device(qkv.device):
+            L.check(self.lib.fvhd_attention(self.handle, C.c_void_p(torch.cuda.current_stream(qkv.device).cuda_stream), qkv.data_ptr(),
+                                            out.data_ptr(), int(batch), int(n_tokens), Cc), self.handle)
+        return out
+
     def mixer(self, x, w3, b3, w7, b7):
         """(y, z) = (dw3x3(x) + b3, dw7x7(y) + b7) on the tcgen05 mixer kernel; x bf16 NHWC [B,H,W,C], weights fp32 tap-major."""
         B, H, W, Cc = x.shape

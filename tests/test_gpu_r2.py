@@ -345,3 +345,30 @@ def test_convffn2_mixed_format_probe(dev):
     ref = r.float() + torch.nn.functional.gelu(z.float() @ w1.float().t() + b1) @ w2.float().t() + b2
     print("mixed-format probe rel-L2", rel_l2(out.float(), ref))
     assert rel_l2(out.float(), ref) < 4e-3
+
+
+# ------------------------------------------------------------------ MHSA core: tcgen05 / TMEM kernel (attention_umma.cuh) vs mma.sync kernel vs torch
+@pytest.mark.parametrize("mode", ["u", "m"])
+@pytest.mark.parametrize("B,N,C", [(1, 1024, 768), (2, 256, 1536), (1, 64, 768), (3, 16, 1536), (1, 2304, 768), (2, 300, 64)])
+def test_attention_core_vs_torch(dev, B, N, C, mode):
+    """softmax((q 32^-1/2) k^T) v per head of 32 (mci.py:675-679).  N = 1024 / 256: stages 3 / 4 at 1024 px; 64 / 16: at 256 px (one partly
+    filled key tile); 2304: 1536 px (18 key tiles, 9 query pairs); 300: ragged tail in keys AND queries."""
+    os.environ["FVHD_ATTN"] = mode
+    try:
+        eng = pkg.Engine(64, 0, 2, 1)
+        eng.gemm(torch.zeros(8, 64, dtype=torch.bfloat16, device=dev), torch.zeros(8, 64, dtype=torch.bfloat16, device=dev))
+    finally:
+        os.environ.pop("FVHD_ATTN", None)
+    g = torch.Generator().manual_seed(N + C + B)
+    qkv = (torch.randn(B * N, 3 * C, generator=g) * 1.5).to(torch.bfloat16)
+    out = eng.attention(qkv.to(dev), B, N)
+    torch.cuda.synchronize()
+    h = C // 32
+    t = qkv.float().reshape(B, N, 3, h, 32).permute(2, 0, 3, 1, 4)
+    q, k, v = t[0], t[1], t[2]
+    ref = ((q * 32 ** -0.5) @ k.transpose(-2, -1)).softmax(-1) @ v
+    ref = ref.transpose(1, 2).reshape(B * N, C)
+    err = rel_l2(out.float(), ref)
+    print(f"attention[{mode}] B={B} N={N} C={C}: rel-L2 {err:.2e}")
+    assert torch.isfinite(out.float()).all()
+    assert err < 6e-3, err                       # bf16 P and bf16 output
