@@ -206,32 +206,35 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap tmQKV /*[B*N, 3C] bf16
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_free[g]);               // S_g is in registers: the next tile's scores may overwrite it
             const int kvalid = N - j * A::KT;                     // keys of this tile that exist (>= 128 except for the last tile)
-            float mx = m;
+            if (kvalid < A::KT) {                                 // warp-uniform: only the last tile can be ragged
 #pragma unroll
-            for (int i = 0; i < 128; ++i) {
-                float v = __uint_as_float(sv[i]) * c;
-                v = i < kvalid ? v : -INFINITY;
-                sv[i] = __float_as_uint(v);
-                mx = fmaxf(mx, v);
+                for (int i = 0; i < 128; ++i) sv[i] = i < kvalid ? sv[i] : 0xff800000u;      // -inf
             }
+            // running max on the RAW scores (the scale c > 0 commutes with max); four independent chains
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 128; i += 4) {
+                mx0 = fmaxf(mx0, __uint_as_float(sv[i])); mx1 = fmaxf(mx1, __uint_as_float(sv[i + 1]));
+                mx2 = fmaxf(mx2, __uint_as_float(sv[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(sv[i + 3]));
+            }
+            const float mx = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c);      // m, mx: scaled (log2 domain)
             const float alpha = ex2_approx(m - mx);               // 0 for the first tile (m = -inf); rescale O to the new max
             m = mx;
-            float rs = 0.f;
 #pragma unroll
             for (int i = 0; i < A::HD; ++i) o[i] *= alpha;
-            // P = exp2(s - m) -> bf16 -> smem: key kk of the tile lives in SW128 block kk / 64, 16-B chunk (kk % 64) / 8 ^ (row & 7)
+            // P = exp2(s c - m) -> bf16 -> smem: key kk of the tile lives in SW128 block kk / 64, 16-B chunk (kk % 64) / 8 ^ (row & 7)
+            float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+            const float nmx = -mx;
 #pragma unroll
             for (int c8 = 0; c8 < 16; ++c8) {
-                uint32_t w[4];
+                float pe[8];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float p0 = ex2_approx(__uint_as_float(sv[c8 * 8 + 2 * e]) - mx);
-                    const float p1 = ex2_approx(__uint_as_float(sv[c8 * 8 + 2 * e + 1]) - mx);
-                    rs += p0 + p1;
-                    w[e] = pack_bf16x2(p0, p1);
-                }
-                *reinterpret_cast<uint4*>(prow + (c8 >> 3) * 16384 + ((((uint32_t)(c8 & 7)) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                for (int e = 0; e < 8; ++e) pe[e] = ex2_approx(fmaf(__uint_as_float(sv[c8 * 8 + e]), c, nmx));
+                rs0 += pe[0] + pe[4]; rs1 += pe[1] + pe[5]; rs2 += pe[2] + pe[6]; rs3 += pe[3] + pe[7];
+                *reinterpret_cast<uint4*>(prow + (c8 >> 3) * 16384 + ((((uint32_t)(c8 & 7)) ^ sw) << 4)) =
+                    make_uint4(pack_bf16x2(pe[0], pe[1]), pack_bf16x2(pe[2], pe[3]), pack_bf16x2(pe[4], pe[5]), pack_bf16x2(pe[6], pe[7]));
             }
+            const float rs = (rs0 + rs1) + (rs2 + rs3);
             l = l * alpha + rs;
             fence_proxy_async_smem();
             tc_fence_before();

@@ -508,7 +508,8 @@ int make_gemm_step(fvhd_handle h, Step* out, const IoBlock* io, int rows_per_ima
     p.tiles_n = (N + p.BN - 1) / p.BN;
     p.ctiles = p.share_b ? ((p.tiles_m + p.cs - 1) / p.cs) * p.tiles_n : p.tiles_m * ((p.tiles_n + p.cs - 1) / p.cs);
     p.split_k = 1; p.kb_per_split = num_kb; p.ws = nullptr; p.counters = nullptr;
-    if (g_use_splitk && p.cs == 1 && h->splitk_ws && 2 * p.ctiles <= h->num_sms && num_kb >= 8 && p.ctiles <= kSplitKTiles) {
+    if (g_use_splitk && p.cs == 1 && D != nullptr && h->splitk_ws && 2 * p.ctiles <= h->num_sms && num_kb >= 8 && p.ctiles <= kSplitKDoneOfs &&
+        N % 4 == 0 && ldd % 4 == 0 && (residual == nullptr || ldr % 4 == 0)) {
         // weight-streaming regime (few output tiles, long K): slice K so that ~all SMs stream weights; >= 4 k-blocks per slice
         int S = h->num_sms / p.ctiles;
         if (S > num_kb / 4) S = num_kb / 4;

@@ -31,6 +31,7 @@ constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KiB
 constexpr int GEMM_EPI_STAGE_BYTES = 32 * 128;                  // per epilogue warp: 32 rows x 64 bf16, SWIZZLE_128B
 constexpr int GEMM_EPI_BIAS_BYTES = 2 * 64 * 4;                 // per epilogue warp: bias of its (up to) two 64-column groups
+constexpr int kSplitKDoneOfs = 2048;                              // counters[tile] = arrivals, counters[2048 + tile] = finished reducers
 constexpr int GEMM_SMEM_BUDGET = 200 * 1024 - GEMM_EPI_WARPS * (GEMM_EPI_STAGE_BYTES + GEMM_EPI_BIAS_BYTES);
 
 struct GemmParams {
@@ -52,9 +53,9 @@ struct GemmParams {
     unsigned long long* trace;   // debug: 16 globaltimer stamps per CTA (nullptr = off)
     int tma_store;           // 1: tmD is valid (D is library memory) -> full 64-column groups leave through TMA
     // Split-K (small-M, weight-streaming GEMMs of stages 3-4 / projector at small batch: a 2 x 12-tile grid cannot keep 148 SMs
-    // streaming weights).  Work item = (tile, k-slice): every CTA accumulates its slice, writes the fp32 partial tile to `ws`
-    // and bumps the tile's counter; the LAST CTA to arrive re-reads all `split_k` partials in slice order (deterministic) and
-    // runs the ordinary epilogue.  Counters are self-resetting.  cs must be 1.
+    // streaming weights).  Work item = (tile, k-slice), ONE per CTA (all co-resident): every CTA accumulates its slice, writes the
+    // fp32 partial tile to `ws`, waits for the tile's other slices, then reduces its own band of 128 / split_k rows (slice order:
+    // deterministic) with the bias / GELU / residual epilogue.  Counters are self-resetting.  cs must be 1, D must be non-null.
     int split_k;             // 1 = off
     int kb_per_split;        // k-blocks per slice
     float* ws;               // [tiles][split_k][128][BN] fp32
@@ -311,7 +312,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const uint32_t lane_addr = tmem_base + (uint32_t)a * acc_stride + ((uint32_t)(q * 32) << 16);
             bool do_epi = true;
             if (S > 1) {
-                // ---- split-K: publish this slice's fp32 partial, then find out whether this CTA is the last slice of the tile
+                // ---- split-K.  (1) publish this slice's fp32 partial tile; (2) wait until all S slices of the tile have published
+                // (the S CTAs are co-resident: the host launches exactly one work item per CTA); (3) every slice CTA reduces a band of
+                // 128 / S rows of the tile -- S coalesced float4 streams, summed in slice order (deterministic) -- applies bias / GELU /
+                // residual and stores bf16.  The reduction is spread over all CTAs instead of serialising on the last arrival.
+                do_epi = false;
+                const int ks = ct - tile * S;
                 float* wsp = p.ws + ((size_t)ct * GEMM_BM + (size_t)(q * 32 + lane)) * (size_t)BN;
                 for (int g = hh; g < ngroups; g += 2) {
                     const int gcol = g * 64;
@@ -328,32 +334,46 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 __threadfence();
                 named_bar_sync(1, GEMM_EPI_WARPS * 32);
                 if (warp == 2 && lane == 0) {
-                    const int old = atomicAdd(p.counters + tile, 1);
-                    const int last = old == S - 1;
-                    if (last) p.counters[tile] = 0;             // self-resetting: every other slice has already arrived
-                    *sflag = last;
+                    atomicAdd(p.counters + tile, 1);
+                    while (*reinterpret_cast<volatile int*>(p.counters + tile) < S) { }
+                    __threadfence();
                 }
                 named_bar_sync(1, GEMM_EPI_WARPS * 32);
-                do_epi = *sflag != 0;
-                if (do_epi) __threadfence();
-            }
-            // accumulator chunk loader: TMEM (ordinary) or the sum of the tile's S partials in slice order (split-K, deterministic)
-            auto load_chunk = [&](int colofs, uint32_t (&dst)[32]) {
-                if (S == 1) { tmem_ld32(lane_addr + (uint32_t)colofs, dst); return; }
-                float accv[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) accv[j] = 0.f;
-                for (int sl = 0; sl < S; ++sl) {
-                    const float4* src = reinterpret_cast<const float4*>(p.ws + ((size_t)(tile * S + sl) * GEMM_BM + (size_t)(q * 32 + lane)) * (size_t)BN + colofs);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 v4 = __ldcg(src + j);
-                        accv[4 * j] += v4.x; accv[4 * j + 1] += v4.y; accv[4 * j + 2] += v4.z; accv[4 * j + 3] += v4.w;
+                const int band = (GEMM_BM + S - 1) / S;
+                const int r_lo = ks * band, r_hi = (r_lo + band) < GEMM_BM ? (r_lo + band) : GEMM_BM;
+                const int c4n = BN >> 2;                                  // float4 per tile row
+                const int et = (int)threadIdx.x - 64;                     // 0..255 over the epilogue warps
+                const float* wt = p.ws + (size_t)tile * S * GEMM_BM * BN;
+                for (int idx = et; idx < (r_hi - r_lo) * c4n; idx += GEMM_EPI_WARPS * 32) {
+                    const int rr = r_lo + idx / c4n, c4 = idx - (idx / c4n) * c4n;
+                    const int grow = m0 + rr, gcol = n0 + 4 * c4;
+                    float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int sl = 0; sl < S; ++sl) {
+                        const float4 v4 = __ldcg(reinterpret_cast<const float4*>(wt + ((size_t)sl * GEMM_BM + rr) * BN) + c4);
+                        acc4.x += v4.x; acc4.y += v4.y; acc4.z += v4.z; acc4.w += v4.w;
+                    }
+                    if (grow < p.M && gcol + 4 <= p.N) {
+                        if (p.bias) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
+                            acc4.x += b4.x; acc4.y += b4.y; acc4.z += b4.z; acc4.w += b4.w;
+                        }
+                        if (p.act == 1) { acc4.x = gelu_erf(acc4.x); acc4.y = gelu_erf(acc4.y); acc4.z = gelu_erf(acc4.z); acc4.w = gelu_erf(acc4.w); }
+                        if (p.residual) {
+                            const uint2 rv = *reinterpret_cast<const uint2*>(p.residual + (size_t)grow * p.ldr + gcol);
+                            const float2 r0 = unpack_bf16x2(rv.x), r1 = unpack_bf16x2(rv.y);
+                            acc4.x += r0.x; acc4.y += r0.y; acc4.z += r1.x; acc4.w += r1.y;
+                        }
+                        *reinterpret_cast<uint2*>(p.D + (size_t)grow * p.ldd + gcol) = make_uint2(pack_bf16x2(acc4.x, acc4.y), pack_bf16x2(acc4.z, acc4.w));
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) dst[j] = __float_as_uint(accv[j]);
-            };
+                // the last slice to finish re-arms the tile's counters for the next launch
+                named_bar_sync(1, GEMM_EPI_WARPS * 32);
+                if (warp == 2 && lane == 0) {
+                    const int done = atomicAdd(p.counters + kSplitKDoneOfs + tile, 1);
+                    if (done == S - 1) { p.counters[tile] = 0; p.counters[kSplitKDoneOfs + tile] = 0; }
+                }
+            }
+            auto load_chunk = [&](int colofs, uint32_t (&dst)[32]) { tmem_ld32(lane_addr + (uint32_t)colofs, dst); };
             int gk = 0;
             for (int g = hh; do_epi && g < ngroups; g += 2, ++gk) {
                 const int gcol = g * 64;                         // first tile column of the group

@@ -69,7 +69,7 @@ def _conv(g, sd, name, cout, cin_per_group, k, gain=1.0, bias_std=0.05, identity
     sd[name + ".bias"] = g.normal((cout,), bias_std)
 
 
-def _convffn(g, sd, p, c):
+def _convffn(g, sd, p, c, gain=1.0):
     # ConvFFN (mci.py:862-927): dw7x7 (no bias) -> BN -> fc1 -> GELU -> fc2
     sd[p + ".conv.conv.weight"] = g.normal((c, 1, 7, 7), 1.0 / 7.0)
     sd[p + ".conv.bn.weight"] = g.uniform((c,), 0.5, 1.5)
@@ -77,13 +77,22 @@ def _convffn(g, sd, p, c):
     sd[p + ".conv.bn.running_mean"] = g.normal((c,), 0.1)
     sd[p + ".conv.bn.running_var"] = g.uniform((c,), 0.5, 1.5)
     sd[p + ".conv.bn.num_batches_tracked"] = torch.zeros((), dtype=torch.int64)
-    _conv(g, sd, p + ".fc1", MLP_RATIO * c, c, 1, gain=1.0)
-    _conv(g, sd, p + ".fc2", c, MLP_RATIO * c, 1, gain=1.0)
+    _conv(g, sd, p + ".fc1", MLP_RATIO * c, c, 1, gain=gain)
+    _conv(g, sd, p + ".fc2", c, MLP_RATIO * c, 1, gain=gain)
 
 
-def tower_state_dict(seed=123):
-    """Reference-keyed fp32 state-dict of MobileCLIPVisionTower (629 entries)."""
+def tower_state_dict(seed=123, variant="a"):
+    """Reference-keyed fp32 state-dict of MobileCLIPVisionTower (629 entries).
+
+    variant "a" (default, all goldens): layer scales U(0.15, 0.8) with fan-in gain 1 on the ConvFFN / attention weights.
+    variant "b": the layer-scale range SURVEY.md 8(d) prescribes, U(0.5, 1.5) for every layer_scale*, with the branch weights
+    scaled down (gain 0.4) -- with gain-1 weights that range makes the activations grow to std 3e4 and the reference's own
+    bf16 run then sits 0.11 from its fp32 run (measured), i.e. it cannot resolve a kernel error.  Variant b keeps the
+    activations O(1) at the survey's scales; it is a second, independent parity case (tests/test_gpu_r2.py)."""
     g = _Gen(seed)
+    vb = variant == "b"
+    ls = (lambda lo, hi: (0.5, 1.5)) if vb else (lambda lo, hi: (lo, hi))
+    bg = 0.4 if vb else 1.0
     sd = OrderedDict()
     P = TOWER_PREFIX
     c0 = EMBED_DIMS[0]
@@ -104,18 +113,18 @@ def tower_state_dict(seed=123):
             for b in range(LAYERS[i]):
                 p = n + f".{b}"
                 if TOKEN_MIXERS[i] == "repmixer":   # RepMixerBlock (mci.py:1042-1113)
-                    sd[p + ".layer_scale"] = g.uniform((c, 1, 1), 0.15, 0.45)
+                    sd[p + ".layer_scale"] = g.uniform((c, 1, 1), *ls(0.15, 0.45))
                     _conv(g, sd, p + ".token_mixer.reparam_conv", c, 1, 3, gain=0.3, identity=True)
-                    _convffn(g, sd, p + ".convffn", c)
+                    _convffn(g, sd, p + ".convffn", c, bg)
                 else:                               # AttentionBlock (mci.py:1116-1192)
-                    sd[p + ".layer_scale_1"] = g.uniform((c, 1, 1), 0.3, 0.8)
-                    sd[p + ".layer_scale_2"] = g.uniform((c, 1, 1), 0.2, 0.6)
+                    sd[p + ".layer_scale_1"] = g.uniform((c, 1, 1), *ls(0.3, 0.8))
+                    sd[p + ".layer_scale_2"] = g.uniform((c, 1, 1), *ls(0.2, 0.6))
                     sd[p + ".norm.weight"] = g.uniform((c,), 0.5, 1.5)
                     sd[p + ".norm.bias"] = g.normal((c,), 0.1)
                     sd[p + ".token_mixer.qkv.weight"] = g.normal((3 * c, c), 1.3 / np.sqrt(c))
-                    sd[p + ".token_mixer.proj.weight"] = g.normal((c, c), 1.0 / np.sqrt(c))
+                    sd[p + ".token_mixer.proj.weight"] = g.normal((c, c), bg / np.sqrt(c))
                     sd[p + ".token_mixer.proj.bias"] = g.normal((c,), 0.05)
-                    _convffn(g, sd, p + ".convffn", c)
+                    _convffn(g, sd, p + ".convffn", c, bg)
     # conv_exp + SE (mci.py:1401-1411, 42-81)
     ce = EMBED_DIMS[-1] * CLS_RATIO
     rd = int(ce * SE_RD)

@@ -372,3 +372,63 @@ def test_attention_core_vs_torch(dev, B, N, C, mode):
     print(f"attention[{mode}] B={B} N={N} C={C}: rel-L2 {err:.2e}")
     assert torch.isfinite(out.float()).all()
     assert err < 6e-3, err                       # bf16 P and bf16 output
+
+
+# ------------------------------------------------------------------ second fixture: the survey's layer-scale range U(0.5, 1.5)
+def test_second_fixture_survey_layer_scales(dev):
+    """oracle/fixture.py variant "b" (every layer_scale* ~ U(0.5, 1.5)): every unit in isolation <= 8e-3, and the whole
+    encode_images within 5e-2 AND within 1.25x of the reference algorithm's own bf16 error on this fixture."""
+    sd = fx.tower_state_dict(variant="b")
+    psd = fx.projector_state_dict(896)
+    pk = pkg.pack_tower(sd)
+    pk.update(pkg.pack_projector(psd))
+    eng = pkg.Engine(256, 896, 2, 1).load(pk, dev)
+    x = fx.synthetic_images(1, 256, seed=9)
+    col = {}
+    ref = orc.encode_images(x, sd, psd, col)
+    prev, worst = None, {}
+    for u in eng.units():
+        name = u["name"]
+        if name == "stem":
+            xin, want = x.to(dev), col["stem"].permute(0, 2, 3, 1)
+        elif name == "conv_exp":
+            xin, want = _nhwc(prev, dev), col["tokens"]
+        elif name == "projector":
+            xin, want = col["tokens"].reshape(1, -1).to(torch.bfloat16).to(dev), ref
+        else:
+            xin, want = _nhwc(prev, dev), col[name].permute(0, 2, 3, 1)
+        got = eng.run_units(u["index"], u["index"], xin, 1)
+        worst[name] = rel_l2(got.float().reshape(-1), want.reshape(-1))
+        prev = col.get(name)
+    bad = {k: v for k, v in worst.items() if v > 8e-3}
+    assert not bad, bad
+    _, proj = eng.forward(x.to(dev), False, True)
+    sdb = {k: (v.to(torch.bfloat16) if v.is_floating_point() else v) for k, v in sd.items()}
+    psdb = {k: v.to(torch.bfloat16) for k, v in psd.items()}
+    with torch.no_grad():
+        prj_b = orc.mm_projector(orc.feature_select(orc.fastvit_forward(x.to(torch.bfloat16), sdb)), psdb)
+    e, eb = rel_l2(proj.float(), ref), rel_l2(prj_b.float(), ref)
+    print(f"fixture b: encode_images rel-L2 {e:.3e} (reference's own bf16 run: {eb:.3e}); worst unit {max(worst.values()):.2e}")
+    assert e < E2E_TOL and e <= 1.25 * eb
+
+
+def test_repmixer_block_large_activations(packed, tower_sd, dev):
+    """The f16 paths inside a RepMixer block (y planes of the mma.sync mixer, packed-half GELU / f16 hidden of the fused ConvFFN,
+    f16 partials of the cluster ConvFFN) keep their accuracy for activations three orders of magnitude above the fixture's
+    (|x| ~ 4e3, well inside the f16 range the reference itself runs in -- predict.py:58 `.half()`), and SATURATE to finite
+    values (cvt.satfinite) instead of producing inf / NaN when an activation leaves the f16 range."""
+    eng = pkg.Engine(256, 896, 2, 1).load(packed, dev)
+    units = {u["name"]: u for u in eng.units()}
+    g = torch.Generator().manual_seed(17)
+    for name, c, hw in (("network.2.3", 192, 32), ("network.4.5", 384, 16)):       # a stage-1 block (fused kernel) and a stage-2 block (cluster kernel)
+        u = units[name]
+        p = fx.TOWER_PREFIX + name
+        for scale, check in ((1e3, True), (1e5, False)):
+            x = (torch.randn(1, c, hw, hw, generator=g) * scale).to(torch.bfloat16)
+            want = orc.repmixer_block(x.float(), tower_sd, p).permute(0, 2, 3, 1).reshape(-1)
+            got = eng.run_units(u["index"], u["index"], _nhwc(x.float(), dev), 1).float().reshape(-1)
+            assert torch.isfinite(got).all(), (name, scale)
+            if check:
+                err = rel_l2(got, want)
+                print(f"{name} x{scale:g}: rel-L2 {err:.2e}")
+                assert err < 8e-3, (name, scale, err)
