@@ -22,7 +22,6 @@ namespace fvhd {
 constexpr int CF_EPI_WARPS = 16;
 constexpr int CF_THREADS = 32 * (2 + CF_EPI_WARPS);          // 576
 constexpr int CF_SLOT = 24576;                               // one weight ring slot
-constexpr int CF_ACC1_COL = 384;                             // TMEM: acc2 at [0, C), acc1[b] at 384 + 64 b
 
 template <int C> struct CfCfg {
     static constexpr int KB = (C + 63) / 64;                 // k-blocks of z / W1 (C = 96: the second one is half zero-filled)
@@ -32,11 +31,15 @@ template <int C> struct CfCfg {
     static constexpr int N2 = C / W2U;                       // N of one MMA2
     static constexpr int KB1 = KB / W1U;                     // k-blocks of W1 per slot
     static constexpr int NSLOT = C == 384 ? 3 : 4;
+    // acc1 / H buffers: MMA1 runs NB - 1 chunks ahead of MMA2, so the GELU epilogue's latency (a1_full -> h_full, ~1.5-2 k cycles
+    // measured) is hidden behind NB - 1 chunks of tensor work instead of one.  C = 384 has neither the TMEM columns nor the smem.
+    static constexpr int NB = C == 384 ? 2 : 4;
+    static constexpr int ACC1_COL = C == 96 ? 128 : C;       // TMEM: acc2 at [0, C), acc1[b] at ACC1_COL + 64 b
     static constexpr int Z_BYTES = KB * GEMM_A_STAGE_BYTES;
-    static constexpr size_t SMEM = (size_t)Z_BYTES + 2 * GEMM_A_STAGE_BYTES + (size_t)NSLOT * CF_SLOT + (size_t)5 * C * 4 + 256 + 1024;
+    static constexpr size_t SMEM = (size_t)Z_BYTES + (size_t)NB * GEMM_A_STAGE_BYTES + (size_t)NSLOT * CF_SLOT + (size_t)5 * C * 4 + 256 + 1024;
     static_assert(KB1 * 64 * 128 <= CF_SLOT && N2 * 128 <= CF_SLOT, "weight slot size");
     static_assert(SMEM <= 227 * 1024, "ConvFFN smem");
-    static_assert(NC % 2 == 0, "acc1 / H double buffering assumes an even chunk count");
+    static_assert(ACC1_COL + NB * 64 <= 512, "TMEM columns");
 };
 
 __host__ __device__ __forceinline__ uint32_t umma_idesc_f16bf16(uint32_t a_bf16, uint32_t b_bf16, uint32_t M, uint32_t N) {
@@ -76,12 +79,13 @@ convffn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
                        const __grid_constant__ CUtensorMap tmW2, const MlpParams p) {
     using Cfg = CfCfg<C>;
     constexpr int KB = Cfg::KB, NC = Cfg::NC, NSLOT = Cfg::NSLOT, W1U = Cfg::W1U, W2U = Cfg::W2U, N2 = Cfg::N2, KB1 = Cfg::KB1;
+    constexpr int NB = Cfg::NB, LA = NB - 1, ACC1 = Cfg::ACC1_COL;
     extern __shared__ uint8_t cf_smem_raw[];
     const uint32_t raw_addr = smem_u32(cf_smem_raw);
     uint8_t* smem = cf_smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
     uint8_t* smemZ = smem;
     uint8_t* smemH = smemZ + Cfg::Z_BYTES;
-    uint8_t* smemW = smemH + 2 * GEMM_A_STAGE_BYTES;
+    uint8_t* smemW = smemH + NB * GEMM_A_STAGE_BYTES;
     float* sb1 = reinterpret_cast<float*>(smemW + (size_t)NSLOT * CF_SLOT);
     float* sb2 = sb1 + 4 * C;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sb2 + C);
@@ -89,11 +93,11 @@ convffn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
     uint64_t* z_empty = bars + 1;            // [1]
     uint64_t* w_full = bars + 2;             // [NSLOT]
     uint64_t* w_empty = w_full + 4;          // [NSLOT]
-    uint64_t* a1_full = w_empty + 4;         // [2]
-    uint64_t* a1_empty = a1_full + 2;        // [2]
-    uint64_t* h_full = a1_empty + 2;         // [2]
-    uint64_t* h_empty = h_full + 2;          // [2]
-    uint64_t* a2_full = h_empty + 2;         // [1]
+    uint64_t* a1_full = w_empty + 4;         // [NB <= 4]
+    uint64_t* a1_empty = a1_full + 4;        // [NB]
+    uint64_t* h_full = a1_empty + 4;         // [NB]
+    uint64_t* h_empty = h_full + 4;          // [NB]
+    uint64_t* a2_full = h_empty + 4;         // [1]
     uint64_t* a2_empty = a2_full + 1;        // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a2_empty + 1);
 
@@ -105,7 +109,7 @@ convffn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
         tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
         mbar_init(z_full, 1); mbar_init(z_empty, 1);
         for (int s = 0; s < NSLOT; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < NB; ++b) {
             mbar_init(&a1_full[b], 1); mbar_init(&a1_empty[b], CF_EPI_WARPS);
             mbar_init(&h_full[b], CF_EPI_WARPS); mbar_init(&h_empty[b], 1);
         }
@@ -141,25 +145,27 @@ convffn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
                     tma_load_2d(dst, &tmW2, j * MLP_NH, u * N2, &w_full[s]);
                 }
             };
-            // slot-load q of a tile's weight stream: W1[0] (W1U slots), then per j = 1..NC-1: W1[j], W2[j-1]; finally W2[NC-1]
-            constexpr int PER = W1U + W2U;
-            constexpr int TOT = NC * PER;
-            auto load_seq = [&](int q) {
-                if (q < W1U) { load_w(false, 0, q); return; }
-                if (q >= TOT - W2U) { load_w(true, NC - 1, q - (TOT - W2U)); return; }
-                const int g = (q - W1U) / PER, r = (q - W1U) % PER;
-                if (r < W1U) load_w(false, g + 1, r); else load_w(true, g, r - W1U);
+            // a tile's weight stream in the MMA warp's consumption order: step t issues W1[t] (t < NC) then W2[t - LA] (t >= LA);
+            // slot-loads [from, to) of that sequence
+            constexpr int TOT = NC * (W1U + W2U);
+            auto run_tile_loads = [&](int from, int to) {
+                int q = 0;
+                for (int t = 0; t < NC + LA; ++t) {
+                    if (t < NC)
+                        for (int u = 0; u < W1U; ++u, ++q) if (q >= from && q < to) load_w(false, t, u);
+                    if (t >= LA)
+                        for (int u = 0; u < W2U; ++u, ++q) if (q >= from && q < to) load_w(true, t - LA, u);
+                }
             };
             int q0 = 0;                                  // weights are constants: first ring fill before the PDL wait
-            if ((int)blockIdx.x < p.tiles_m)
-                for (; q0 < NSLOT; ++q0) load_seq(q0);
+            if ((int)blockIdx.x < p.tiles_m) { q0 = NSLOT < TOT ? NSLOT : TOT; run_tile_loads(0, q0); }
             pdl_wait();
             int ti = 0;
             for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x, ++ti) {
                 mbar_wait(z_empty, ((uint32_t)ti & 1u) ^ 1u);
                 mbar_expect_tx(z_full, (uint32_t)Cfg::Z_BYTES);
                 for (int kb = 0; kb < KB; ++kb) tma_load_2d(smemZ + (size_t)kb * GEMM_A_STAGE_BYTES, &tmZ, kb * 64, tile * GEMM_BM, z_full);
-                for (int q = ti == 0 ? q0 : 0; q < TOT; ++q) load_seq(q);
+                run_tile_loads(ti == 0 ? q0 : 0, TOT);
             }
         }
     } else if (warp == 1) {
@@ -170,7 +176,6 @@ convffn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
         const uint64_t dz0 = umma_desc_sw128(smem_u32(smemZ));
         const uint64_t dh0 = umma_desc_sw128(smem_u32(smemH));
         const uint64_t dw0 = umma_desc_sw128(smem_u32(smemW));
-        constexpr int half_nc = NC / 2;
         int wit = 0, ti = 0;
         auto take_slot = [&]() -> int {
             const int s = wit % NSLOT;
@@ -179,61 +184,60 @@ convffn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
             mbar_wait(&w_full[s], ph);
             return s;
         };
-        auto mma2 = [&](int j, int ti_) {    // acc2 (+)= H[j&1] . W2[:, chunk j]^T
-            const int b = j & 1;
-            const uint32_t use = (uint32_t)(ti_ * half_nc + (j >> 1));
-            mbar_wait(&h_full[b], use & 1u);
-            if (j == 0) mbar_wait(a2_empty, ((uint32_t)ti_ & 1u) ^ 1u);     // previous tile's epilogue drained acc2
-            const uint64_t da = dh0 + (uint64_t)(b * (GEMM_A_STAGE_BYTES >> 4));
-#pragma unroll
-            for (int u = 0; u < W2U; ++u) {
-                const int s = take_slot();
-                tc_fence_after();
-                const uint64_t db = dw0 + (uint64_t)(s * (CF_SLOT >> 4));
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (elect_one()) umma_bf16(tm + (uint32_t)(u * N2), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (j | k) != 0 ? 1u : 0u);
-                if (elect_one()) umma_commit(&w_empty[s]);
-                __syncwarp();
-            }
-            if (elect_one()) umma_commit(&h_empty[b]);
-            __syncwarp();
-        };
         for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x, ++ti) {
             mbar_wait(z_full, (uint32_t)ti & 1u);
 #pragma unroll 1
-            for (int j = 0; j < NC; ++j) {
-                const int b = j & 1;
-                const uint32_t use = (uint32_t)(ti * half_nc + (j >> 1));
-                mbar_wait(&a1_empty[b], (use & 1u) ^ 1u);                    // epilogue has drained acc1[b]
-                const uint32_t acc1 = tm + CF_ACC1_COL + (uint32_t)(b * MLP_NH);
+            for (int t = 0; t < NC + LA; ++t) {
+                if (t < NC) {        // ---- MMA1(t): acc1[b] = z . W1[t]^T
+                    const int gj = ti * NC + t, b = gj % NB;
+                    mbar_wait(&a1_empty[b], ((uint32_t)(gj / NB) & 1u) ^ 1u);    // epilogue has drained acc1[b]
+                    const uint32_t acc1 = tm + ACC1 + (uint32_t)(b * MLP_NH);
 #pragma unroll
-                for (int u = 0; u < W1U; ++u) {
-                    const int s = take_slot();
-                    tc_fence_after();
-                    const uint64_t db = dw0 + (uint64_t)(s * (CF_SLOT >> 4));
+                    for (int u = 0; u < W1U; ++u) {
+                        const int s = take_slot();
+                        tc_fence_after();
+                        const uint64_t db = dw0 + (uint64_t)(s * (CF_SLOT >> 4));
 #pragma unroll
-                    for (int kk = 0; kk < KB1; ++kk) {
-                        const int kb = KB1 * u + kk;
-                        const int ksteps = (C - kb * 64) >= 64 ? 4 : (C - kb * 64) / 16;     // C = 96: the second k-block has 2 steps
+                        for (int kk = 0; kk < KB1; ++kk) {
+                            const int kb = KB1 * u + kk;
+                            const int ksteps = (C - kb * 64) >= 64 ? 4 : (C - kb * 64) / 16;     // C = 96: the second k-block has 2 steps
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (k < ksteps && elect_one())
-                                umma_bf16(acc1, dz0 + (uint64_t)(kb * (GEMM_A_STAGE_BYTES >> 4) + 2 * k), db + (uint64_t)(kk * (64 * 128 >> 4) + 2 * k), idesc1,
-                                          (u | kk | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < 4; ++k) {
+                                if (k < ksteps && elect_one())
+                                    umma_bf16(acc1, dz0 + (uint64_t)(kb * (GEMM_A_STAGE_BYTES >> 4) + 2 * k), db + (uint64_t)(kk * (64 * 128 >> 4) + 2 * k), idesc1,
+                                              (u | kk | k) != 0 ? 1u : 0u);
+                            }
                         }
+                        if (elect_one()) umma_commit(&w_empty[s]);
+                        __syncwarp();
                     }
-                    if (elect_one()) umma_commit(&w_empty[s]);
+                    if (elect_one()) {
+                        umma_commit(&a1_full[b]);
+                        if (t == NC - 1) umma_commit(z_empty);                   // z tile no longer needed
+                    }
                     __syncwarp();
                 }
-                if (elect_one()) {
-                    umma_commit(&a1_full[b]);
-                    if (j == NC - 1) umma_commit(z_empty);                   // z tile no longer needed
+                if (t >= LA) {       // ---- MMA2(j): acc2 (+)= H[b] . W2[:, chunk j]^T, LA chunks behind MMA1
+                    const int j = t - LA;
+                    const int gj = ti * NC + j, b = gj % NB;
+                    mbar_wait(&h_full[b], (uint32_t)(gj / NB) & 1u);
+                    if (j == 0) mbar_wait(a2_empty, ((uint32_t)ti & 1u) ^ 1u);   // previous tile's epilogue drained acc2
+                    const uint64_t da = dh0 + (uint64_t)(b * (GEMM_A_STAGE_BYTES >> 4));
+#pragma unroll
+                    for (int u = 0; u < W2U; ++u) {
+                        const int s = take_slot();
+                        tc_fence_after();
+                        const uint64_t db = dw0 + (uint64_t)(s * (CF_SLOT >> 4));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (elect_one()) umma_bf16(tm + (uint32_t)(u * N2), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (j | k) != 0 ? 1u : 0u);
+                        if (elect_one()) umma_commit(&w_empty[s]);
+                        __syncwarp();
+                    }
+                    if (elect_one()) umma_commit(&h_empty[b]);
+                    __syncwarp();
                 }
-                __syncwarp();
-                if (j >= 1) mma2(j - 1, ti);
             }
-            mma2(NC - 1, ti);
             if (elect_one()) umma_commit(a2_full);
             __syncwarp();
         }
@@ -241,7 +245,6 @@ convffn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
         // ---------------- 16 epilogue warps: lane quarter q == 32 tile rows (hardware: warp % 4); k4 = 16-column slice of a chunk
         const int q = warp & 3;
         const int k4 = (warp - 2) >> 2;
-        constexpr int half_nc = NC / 2;
         constexpr int CW = C / 4;                      // acc2 columns finished by this warp: [k4 * CW, +CW)
         const int row_in_tile = q * 32 + lane;
         const uint32_t sw = (uint32_t)(lane & 7);
@@ -254,14 +257,14 @@ convffn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
             // ---- epilogue 1 per hidden chunk: columns [16 k4, +16) of the 64-wide chunk -> GELU -> f16 -> H[b]
 #pragma unroll 1
             for (int j = 0; j < NC; ++j) {
-                const int b = j & 1;
-                const uint32_t use = (uint32_t)(ti * half_nc + (j >> 1));
+                const int gj = ti * NC + j, b = gj % NB;
+                const uint32_t use = (uint32_t)(gj / NB);
                 const float4* bb = reinterpret_cast<const float4*>(sb1 + j * MLP_NH + k4 * 16);
                 const float4 bv0 = bb[0], bv1 = bb[1], bv2 = bb[2], bv3 = bb[3];
                 mbar_wait(&a1_full[b], use & 1u);
                 tc_fence_after();
                 uint32_t r[16];
-                tmem_ld16(lane_base + CF_ACC1_COL + (uint32_t)(b * MLP_NH + k4 * 16), r);
+                tmem_ld16(lane_base + ACC1 + (uint32_t)(b * MLP_NH + k4 * 16), r);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();

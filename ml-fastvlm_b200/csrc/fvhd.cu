@@ -280,8 +280,8 @@ int g_gemm_max_cs = 1;        // FVHD_GEMM_CS=1|2|4 caps the GEMM cluster size. 
 bool g_use_cluster_mlp = true; // FVHD_NO_CLUSTER_MLP=1: stage-2 (C = 384) ConvFFN as two GEMM launches instead of the 4-CTA-cluster kernel
 bool g_use_fused_mlp = true;  // FVHD_NO_FUSED_MLP=1: ConvFFN as two GEMM launches (reference path of the bit-exactness test)
 const int g_convffn_default = 2;
-const char g_attn_default = 'm';
-char g_attn_mode = 'm';        // FVHD_ATTN=u: tcgen05 / TMEM attention core (attention_umma.cuh); m: mma.sync kernel (stem_attn_se.cuh)
+const char g_attn_default = 'a';
+char g_attn_mode = 'a';        // FVHD_ATTN=a (default): tcgen05 / TMEM core (attention_umma.cuh) from 512 tokens, mma.sync below; u / m force one
 int g_convffn_gen = 1;         // FVHD_CONVFFN=2 (default): second-generation fused ConvFFN kernel (convffn.cuh); 1: mlp_fused (C <= 192) / two GEMMs
 char g_mixer_mode = 't';       // FVHD_MIXER=t: mma.sync 7x7 (mixer_tc.cuh, default); 2: both convs on mma.sync, 16 ch per CTA (mixer_tc2.cuh); u: tcgen05 diagonal-tap mixer (mixer_umma.cuh: correct, but
                                // smem-A-read bound -- 602 vs 434 us/img at batch 32, profiles/r02_*); f: FMA pipes (dwconv.cuh)
@@ -554,6 +554,9 @@ int make_gemm_step(fvhd_handle h, Step* out, const IoBlock* io, int rows_per_ima
     }
     const int nclusters = p.ctiles < resident ? p.ctiles : resident;
     const dim3 grid((unsigned)(nclusters * p.cs));
+    if (getenv("FVHD_DEBUG_PLAN"))
+        fprintf(stderr, "[fvhd] gemm M=%d N=%d K=%d BN=%d stages=%d tiles=%dx%d split_k=%d kb/slice=%d items=%d grid=%u tma_store=%d act=%d\n", M, N, K, p.BN, p.stages,
+                p.tiles_m, p.tiles_n, p.split_k, p.kb_per_split, p.ctiles, grid.x, p.tma_store, act);
     const int cs = p.cs;
     *out = [=](cudaStream_t s, const RunCtx&) -> cudaError_t {
         return launch_kc(cs, gemm_bf16_tcgen05_kernel, grid, dim3(GEMM_THREADS), smem, s, ta, tb, td, p);
@@ -770,13 +773,18 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
             const int TH = small ? 8 : 16;
             const int tx = (W + 15) / 16, ty = (H + TH - 1) / TH;
             const dim3 grid(tx * ty, c / DW_CG, batch);
+            // mixer_tc: persistent CTAs, ~two per SM in total, each bound to one 32-channel group and walking that group's (image, tile) items
+            int per_group = (2 * h->num_sms) / (c / DW_CG);       // floor: a CTA beyond the resident slots would run its whole item loop as a second wave
+            if (per_group < 1) per_group = 1;
+            if (per_group > tx * ty * batch) per_group = tx * ty * batch;
+            const dim3 grid_tc(per_group, c / DW_CG, 1);
             bf16 *y = bf.Y, *z = bf.Z;
             CUtensorMap tmx;
             if ((rc = make_tmap_nhwc(h, &tmx, in, batch, H, W, c, small ? MixCfgT<8, 16>::XP : MixCfgT<16, 16>::XP,
                                      small ? MixCfgT<8, 16>::XH : MixCfgT<16, 16>::XH)) != FVHD_OK) return rc;
             static_assert(MixTc::XP == MixCfgT<16, 16>::XP && MixTc::XH == MixCfgT<16, 16>::XH, "same TMA box for both 16x16 kernels");
             pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
-                if (tc) return launch_k(repmixer_tc_kernel, grid, dim3(MixTc::NT), MixTc::SMEM, s, tmx, y, z, w3, b3, w7, b7, H, W, c, tx);
+                if (tc) return launch_k(repmixer_tc_kernel, grid_tc, dim3(MixTc::NT), MixTc::SMEM, s, tmx, y, z, w3, b3, w7, b7, H, W, c, tx, batch);
                 if (wide) return launch_k(repmixer_dw_kernel<16, 16, 512, 6, 4, 2>, grid, dim3(512), MixCfgT<16, 16>::SMEM, s, tmx, y, z, w3, b3, w7, b7, H, W, c, tx);
                 if (small) return launch_k(repmixer_dw_kernel<8, 16, 128>, grid, dim3(128), MixCfgT<8, 16>::SMEM, s, tmx, y, z, w3, b3, w7, b7, H, W, c, tx);
                 return launch_k(repmixer_dw_kernel<16, 16, 256>, grid, dim3(256), MixCfgT<16, 16>::SMEM, s, tmx, y, z, w3, b3, w7, b7, H, W, c, tx);
@@ -819,7 +827,9 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
             }, "layernorm_channel_kernel", U, 0.0, 4.0 * Md * c);
             if ((rc = add_gemm(h, pl, U, t1, c, WB(h, p + "qkv.w"), nullptr, nullptr, 0, qkv, 3 * c, M, 3 * c, c, 0)) != FVHD_OK) return rc;
             const float sl2 = 0.17677669529663687f * 1.4426950408889634f;   // 32^-0.5 * log2(e)
-            if (g_attn_mode == 'u') {       // tcgen05 / TMEM flash attention (attention_umma.cuh)
+            // auto: tcgen05 / TMEM kernel from 512 tokens (one CTA = 256 queries x 1 head: at N = 256 there are too few CTAs and the
+            // mma.sync kernel's finer grid wins -- measured 12.3 vs 10.5 us at batch 1, 86 vs 84 us at batch 32)
+            if (g_attn_mode == 'u' || (g_attn_mode == 'a' && N >= 512)) {       // tcgen05 / TMEM flash attention (attention_umma.cuh)
                 Step as;
                 if ((rc = make_attention_umma_step(h, &as, qkv, t1, batch, N, c, sl2)) != FVHD_OK) return rc;
                 pl.add(as, "attention_umma_kernel", U, 4.0 * batch * (double)N * N * c, 8.0 * Md * c);

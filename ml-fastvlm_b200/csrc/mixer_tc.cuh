@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(MixTc::NT, 2)
 repmixer_tc_kernel(const __grid_constant__ CUtensorMap tmX /*x: NHWC, box {32, XP, XH, 1}*/, bf16* __restrict__ y, bf16* __restrict__ z,
                    const float* __restrict__ w3 /*[9][C]*/, const float* __restrict__ b3,
                    const float* __restrict__ w7 /*[49][C], BN folded*/, const float* __restrict__ b7,
-                   int H, int W, int C, int tiles_x) {
+                   int H, int W, int C, int tiles_x, int batch) {
     using Cfg = MixTc;
     constexpr int NT = Cfg::NT, TOH = Cfg::TOH, TOW = Cfg::TOW;
     extern __shared__ __align__(128) uint32_t dw_smem[];
@@ -73,10 +73,11 @@ repmixer_tc_kernel(const __grid_constant__ CUtensorMap tmX /*x: NHWC, box {32, X
     uint64_t* bar = reinterpret_cast<uint64_t*>(b7s + DW_CG);
 
     pdl_launch_dependents();
-    const int b = blockIdx.z;
+    // persistent over the spatial tiles of ONE 32-channel group: the constants (3x3 taps, biases, 7x7 pair table) are staged once
+    // per CTA; blockIdx.x walks items (image, tile) = blockIdx.x, blockIdx.x + gridDim.x, ...
     const int c0 = blockIdx.y * DW_CG;
-    const int ty0 = (blockIdx.x / tiles_x) * TOH;
-    const int tx0 = (blockIdx.x % tiles_x) * TOW;
+    const int tiles_per_img = tiles_x * ((H + TOH - 1) / TOH);
+    const int n_items = tiles_per_img * batch;
 
     if (threadIdx.x == 0) {
         MIX_TRACE(0);
@@ -104,15 +105,20 @@ repmixer_tc_kernel(const __grid_constant__ CUtensorMap tmX /*x: NHWC, box {32, X
         ptab[r * Cfg::PTAB_PITCH + c] = pack_f16x2_sat(lo, hi);
     }
     __syncthreads();                  // pair table built; the x tile region may be overwritten by the TMA load
+    pdl_wait();                       // x is the predecessor's output; also orders this thread's global writes (y, z) after it
+    uint32_t xphase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int b = item / tiles_per_img;
+    const int tl_ = item - b * tiles_per_img;
+    const int ty0 = (tl_ / tiles_x) * TOH;
+    const int tx0 = (tl_ % tiles_x) * TOW;
     if (threadIdx.x == 0) {
-        MIX_TRACE(1);
-        pdl_wait();                   // x is the predecessor's output
         MIX_TRACE(2);
         mbar_expect_tx(bar, Cfg::X_WORDS * 4);
         tma_load_4d(sx, &tmX, c0, tx0 - 4, ty0 - 4, b, bar);
     }
-    mbar_wait(bar, 0);
-    pdl_wait();                       // orders this thread's global writes (y, z) after the predecessor
+    mbar_wait(bar, xphase);
+    xphase ^= 1u;
     if (threadIdx.x == 0) MIX_TRACE(3);
 
     // phase 1: y = dw3x3(x) + b on the 22 x 22 region; zero outside the image (the 7x7's zero padding)
@@ -229,6 +235,8 @@ repmixer_tc_kernel(const __grid_constant__ CUtensorMap tmX /*x: NHWC, box {32, X
     }
     if (threadIdx.x == 0) MIX_TRACE(6);
     if (threadIdx.x == NT - 1) MIX_TRACE(7);
+    __syncthreads();                  // the staging tile (aliasing the x tile) has been read: the next item's TMA load may land
+    }   // item loop
 }
 
 }  // namespace fvhd

@@ -5,13 +5,15 @@ profiles/gemm_dram_traffic.json (DRAM bytes per tcgen05 launch).  One forward = 
 usage: make_profile_summary.py <tag> <bench.json> <launches.csv> [notes.md]"""
 import collections, csv, json, os, re, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-TC = ("gemm_bf16_tcgen05_kernel", "mlp_cluster_tcgen05_kernel", "mlp_fused_tcgen05_kernel")
+TC = ("gemm_bf16_tcgen05_kernel", "mlp_cluster_tcgen05_kernel", "mlp_fused_tcgen05_kernel", "convffn_tcgen05_kernel", "attention_umma_kernel",
+      "repmixer_umma_kernel")
 
 
 def short(name):
     n = name.replace("fvhd::", "")
-    n = re.sub(r"\(.*", "", n)
     n = re.sub(r"^void ", "", n)
+    n = re.sub(r"<.*", "", n) if n.startswith("convffn") else n
+    n = re.sub(r"\(.*", "", n)
     return n[:40]
 
 
@@ -38,7 +40,7 @@ def main():
         a["wr"] += d.get("dram__bytes_write.sum", 0.0)
         a["tw"] += d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 0.0) * d.get("gpu__time_duration.sum", 0.0)
     tot = sum(a["ns"] for a in agg.values())
-    out = [f"# Round 1, measurement {tag[-1].upper()} ({tag})", ""]
+    out = [f"# {tag}: bench line + ncu launch list", ""]
     out.append(f"* value **{bench['value']:.1f} {bench['unit']}** ({bench['ms_per_step']:.3f} ms/step), e2e {bench['e2e']['value']:.1f} "
                f"({bench['e2e']['ms_per_step']:.3f} ms incl. {bench['e2e']['h2d_bytes_per_step'] / 1e6:.1f} MB H2D + {bench['e2e']['d2h_bytes_per_step'] / 1e6:.2f} MB D2H), "
                f"clocks {bench.get('clocks')}")
@@ -58,7 +60,7 @@ def main():
         json.dump({"bytes_per_launch": per, "algorithmic_bytes_per_launch": alg, "launches": len(tcl),
                    "source": f"profiles/{os.path.basename(csv_path)}: mean dram__bytes_read.sum + dram__bytes_write.sum over the tcgen05 launches "
                              "(GEMM + fused ConvFFN kernels) of one forward (B=1, 1024 px; ncu flushes caches between kernels, so operands come from "
-                             "HBM once; outputs stay in L2)"}, open(os.path.join(ROOT, "profiles", "gemm_dram_traffic.json"), "w"), indent=1)
+                             "HBM once; outputs stay in L2)"}, open(os.path.join(ROOT, "profiles", "r02_tc_dram_traffic.json"), "w"), indent=1)
         out.append(f"* DRAM traffic of the tcgen05 launches (ncu, cold): {per / 1e6:.2f} MB per launch" + (f" vs algorithmic {alg / 1e6:.2f} MB" if alg else ""))
     out += ["", f"## ncu launch list, one forward ({len(fwd)} kernels between two set_io_kernel launches; cold-cache, serialised -> compare shares)", "",
             "| kernel | launches | total us | share | avg us | DRAM rd MB | DRAM wr MB | tensor-pipe active % (time-weighted) |", "|---|---|---|---|---|---|---|---|"]
