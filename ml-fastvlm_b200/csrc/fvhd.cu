@@ -460,12 +460,12 @@ int make_mixer_umma_step(fvhd_handle h, Step* st, const bf16* x, bf16* y, bf16* 
 //   mma  = num_kb * 4 * (128 * BN / 256)          (tcgen05 M=128: 128*N/256 cycles per K=16 instruction)
 //   epi  = 128 * BN * (GELU ? 10 : 6) / 256       (8 epilogue warps)
 //   tile = max(load, mma, epi) + 400 ;  total = rounds * tile, rounds = ceil(cluster_tiles / resident_clusters)
-struct GemmCfg { int bn, cs, share_b; long cost; };
-GemmCfg pick_gemm_cfg(int M, int N, int K, int act, int num_sms) {
+struct GemmCfg { int bn, cs, share_b; long cost; int split; };
+GemmCfg pick_gemm_cfg(int M, int N, int K, int act, int num_sms, bool allow_split = false) {
     const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
     const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
     const int cands[5] = {256, 128, 96, 64, 32};
-    GemmCfg best{128, 1, 0, -1};
+    GemmCfg best{128, 1, 0, -1, 1};
     for (int bn : cands) {
         if (bn == 96 && N % 96) continue;               // 96 only when it divides N (C = 96 / 192 / 384 layers)
         if (bn == 256 && N % 256) continue;
@@ -486,7 +486,21 @@ GemmCfg pick_gemm_cfg(int M, int N, int K, int act, int num_sms) {
                 long tile = load > mma ? load : mma;
                 if (epi > tile) tile = epi;
                 const long cost = rounds * (tile + 400);
-                if (best.cost < 0 || cost < best.cost) best = GemmCfg{bn, cs, share_b, cost};
+                if (best.cost < 0 || cost < best.cost) best = GemmCfg{bn, cs, share_b, cost, 1};
+                // split-K variant (weight-streaming regime): S k-slices per tile, one work item per CTA, distributed reduction;
+                // overhead = fp32 partial tile written + re-read (at the same ~36 B/clk) + the arrival wait
+                if (allow_split && cs == 1 && 2 * ctiles <= num_sms && num_kb >= 8) {
+                    int S = num_sms / (int)ctiles;
+                    if (S > num_kb / 4) S = num_kb / 4;
+                    while (S > 1 && (size_t)ctiles * S * GEMM_BM * bn * sizeof(float) > kSplitKWsBytes) --S;
+                    if (S > 1) {
+                        const int kbs = (num_kb + S - 1) / S;
+                        S = (num_kb + kbs - 1) / kbs;
+                        const long ld_s = (long)kbs * bytes_kb / 36, mma_s = (long)kbs * 4 * (128 * bn / 256);
+                        const long cost_s = (ld_s > mma_s ? ld_s : mma_s) + 400 + 2 * (128L * bn * 4 / 36) + 2000;
+                        if (cost_s < best.cost) best = GemmCfg{bn, 1, 0, cost_s, S};
+                    }
+                }
             }
         }
     }
@@ -497,8 +511,9 @@ GemmCfg pick_gemm_cfg(int M, int N, int K, int act, int num_sms) {
 int make_gemm_step(fvhd_handle h, Step* out, const IoBlock* io, int rows_per_image, const bf16* A, int lda, const bf16* W, const float* bias, const bf16* residual, int ldr,
                    bf16* D, int ldd, int M, int N, int K, int act) {
     if (N % 8 || K % 8) return fail(h, FVHD_ERR_INVALID, "GEMM N (%d) and K (%d) must be multiples of 8", N, K);
-    GemmCfg c = pick_gemm_cfg(M, N, K, act, h->num_sms);
-    if (g_force_bn) { c.bn = g_force_bn; c.cs = 1; c.share_b = 0; }
+    const bool can_split = g_use_splitk && D != nullptr && h->splitk_ws && N % 4 == 0 && ldd % 4 == 0 && (residual == nullptr || ldr % 4 == 0);
+    GemmCfg c = pick_gemm_cfg(M, N, K, act, h->num_sms, can_split);
+    if (g_force_bn) { c.bn = g_force_bn; c.cs = 1; c.share_b = 0; c.split = 1; }
     GemmParams p{};
     p.M = M; p.N = N; p.K = K;
     p.BN = c.bn; p.cs = c.cs; p.share_b = c.share_b;
@@ -508,18 +523,10 @@ int make_gemm_step(fvhd_handle h, Step* out, const IoBlock* io, int rows_per_ima
     p.tiles_n = (N + p.BN - 1) / p.BN;
     p.ctiles = p.share_b ? ((p.tiles_m + p.cs - 1) / p.cs) * p.tiles_n : p.tiles_m * ((p.tiles_n + p.cs - 1) / p.cs);
     p.split_k = 1; p.kb_per_split = num_kb; p.ws = nullptr; p.counters = nullptr;
-    if (g_use_splitk && p.cs == 1 && D != nullptr && h->splitk_ws && 2 * p.ctiles <= h->num_sms && num_kb >= 8 && p.ctiles <= kSplitKDoneOfs &&
-        N % 4 == 0 && ldd % 4 == 0 && (residual == nullptr || ldr % 4 == 0)) {
-        // weight-streaming regime (few output tiles, long K): slice K so that ~all SMs stream weights; >= 4 k-blocks per slice
-        int S = h->num_sms / p.ctiles;
-        if (S > num_kb / 4) S = num_kb / 4;
-        while (S > 1 && (size_t)p.ctiles * S * GEMM_BM * p.BN * sizeof(float) > kSplitKWsBytes) --S;
-        if (S > 1) {
-            const int kbs = (num_kb + S - 1) / S;
-            S = (num_kb + kbs - 1) / kbs;
-            p.split_k = S; p.kb_per_split = kbs; p.ws = h->splitk_ws; p.counters = h->splitk_cnt;
-            p.ctiles *= S;                      // work items = (tile, k-slice)
-        }
+    if (c.split > 1 && p.ctiles <= kSplitKDoneOfs) {
+        const int kbs = (num_kb + c.split - 1) / c.split;
+        p.split_k = (num_kb + kbs - 1) / kbs; p.kb_per_split = kbs; p.ws = h->splitk_ws; p.counters = h->splitk_cnt;
+        p.ctiles *= p.split_k;                      // work items = (tile, k-slice), one per CTA
     }
     p.trace = g_gemm_trace;
     p.D = D; p.io = io; p.rows_per_image = rows_per_image > 0 ? rows_per_image : 1; p.ldd = ldd; p.bias = bias; p.residual = residual; p.ldr = ldr; p.act = act;
