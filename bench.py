@@ -45,8 +45,8 @@ UNIT = "images/s"
 CONFIG4_BATCH = 256     # BASELINE.json configs[3]
 CONFIG4_PASS = 32       # images per library pass (workspace 113 MB per image)
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}    # /opt/skills/guides/B200_PROFILING.md fallback
-TC_KERNELS = ("gemm_bf16_tcgen05_kernel", "mlp_cluster_tcgen05_kernel", "mlp_fused_tcgen05_kernel", "mlp_pair_tcgen05_kernel",
-              "repmixer_umma_kernel")
+TC_KERNELS = ("gemm_bf16_tcgen05_kernel", "convffn_tcgen05_kernel", "mlp_cluster_tcgen05_kernel", "mlp_fused_tcgen05_kernel",
+              "attention_umma_kernel", "repmixer_umma_kernel")
 
 
 def load_peaks():
