@@ -24,6 +24,8 @@
 #include "mixer_tc.cuh"
 #include "mixer_umma.cuh"
 #include "mixer_tc2.cuh"
+#include "mixer_tz.cuh"
+#include "stem2.cuh"
 #include "convffn.cuh"
 #include "attention_umma.cuh"
 
@@ -87,6 +89,7 @@ struct fvhd_handle_s {
     size_t ws_bytes = 0;
     EncodeTiledFn encode = nullptr;
     int num_sms = 148;
+    int tz_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // [cs]: resident cs-CTA clusters of repmixer_tz_kernel (cs = 2, 4, 8)
     int mlpc_clusters = 0;        // resident 4-CTA clusters of mlp_cluster_tcgen05_kernel (cudaOccupancyMaxActiveClusters)
     bool use_graph = true;
     cudaStream_t cap_stream = nullptr;   // private stream used only to capture graphs (the legacy default stream cannot be captured)
@@ -283,7 +286,9 @@ const int g_convffn_default = 2;
 const char g_attn_default = 'a';
 char g_attn_mode = 'a';        // FVHD_ATTN=a (default): tcgen05 / TMEM core (attention_umma.cuh) from 512 tokens, mma.sync below; u / m force one
 int g_convffn_gen = 1;         // FVHD_CONVFFN=2 (default): second-generation fused ConvFFN kernel (convffn.cuh); 1: mlp_fused (C <= 192) / two GEMMs
-char g_mixer_mode = 't';       // FVHD_MIXER=t: mma.sync 7x7 (mixer_tc.cuh, default); 2: both convs on mma.sync, 16 ch per CTA (mixer_tc2.cuh); u: tcgen05 diagonal-tap mixer (mixer_umma.cuh: correct, but
+int g_stem_gen = 2;            // FVHD_STEM=2 (default): stem2.cuh (persistent, packed-half GELUs, 16-B patch loads); 1: first-generation stem_kernel
+char g_mixer_mode = 'z';       // FVHD_MIXER=z (default): 7x7 as Toeplitz products on tcgen05 (mixer_tz.cuh); t: mma.sync 7x7 (mixer_tc.cuh, the round-1 / early
+                               // round-2 default); 2: both convs on mma.sync, 16 ch per CTA (mixer_tc2.cuh); u: tcgen05 diagonal-tap mixer (mixer_umma.cuh: correct, but
                                // smem-A-read bound -- 602 vs 434 us/img at batch 32, profiles/r02_*); f: FMA pipes (dwconv.cuh)
 unsigned long long* g_gemm_trace = nullptr;   // fvhd_debug_gemm_trace: device buffer, 16 stamps per CTA
 int g_force_bn = 0;                            // fvhd_debug_gemm_trace: force the N tile (0 = cost model)
@@ -296,7 +301,9 @@ cudaError_t launch_kc(int cluster, void (*kernel)(KArgs...), dim3 grid, dim3 blo
     cfg.stream = st;
     cudaLaunchAttribute at[2];
     int n = 0;
-    if (g_use_pdl) {
+    const bool no_pdl = cluster <= 0;    // cluster <= 0: plain stream order for this launch (no programmatic early start); |cluster| = cluster size
+    if (cluster < 0) cluster = -cluster;
+    if (g_use_pdl && !no_pdl) {
         at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[n].val.programmaticStreamSerializationAllowed = 1;
         ++n;
@@ -362,7 +369,21 @@ int ensure_cuda(fvhd_handle h) {
     CUDA_TRY(h, set_smem(repmixer_tc_kernel, MixTc::SMEM));
     CUDA_TRY(h, set_smem(repmixer_umma_kernel, MixU::SMEM));
     CUDA_TRY(h, set_smem(repmixer_tc2_kernel, MixT2::SMEM));
-    { const char* e = getenv("FVHD_MIXER"); g_mixer_mode = (e && e[0]) ? e[0] : 't'; }
+    CUDA_TRY(h, set_smem(repmixer_tz_kernel, MixZ::SMEM));
+    for (int cs = 2; cs <= 8; cs *= 2) {   // how many sibling clusters of the Toeplitz mixer can be resident at once (GPC granularity)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(prop.multiProcessorCount / cs * cs));
+        cfg.blockDim = dim3(MixZ::THREADS);
+        cfg.dynamicSmemBytes = MixZ::SMEM;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, repmixer_tz_kernel, &cfg) != cudaSuccess) { nc = 0; (void)cudaGetLastError(); }
+        h->tz_clusters[cs] = nc;
+    }
+    { const char* e = getenv("FVHD_MIXER"); g_mixer_mode = (e && e[0]) ? e[0] : 'z'; }
     { const char* e = getenv("FVHD_ATTN"); g_attn_mode = (e && e[0]) ? e[0] : g_attn_default; }
     CUDA_TRY(h, set_smem(attention_umma_kernel, AttU::SMEM));
     { const char* e = getenv("FVHD_CONVFFN"); g_convffn_gen = (e && e[0] == '2') ? 2 : (e && e[0] == '1') ? 1 : g_convffn_default; }
@@ -375,6 +396,10 @@ int ensure_cuda(fvhd_handle h) {
     CUDA_TRY(h, set_smem(stem_kernel<float>, STEM_SMEM));
     CUDA_TRY(h, set_smem(stem_kernel<__half>, STEM_SMEM));
     CUDA_TRY(h, set_smem(stem_kernel<bf16>, STEM_SMEM));
+    CUDA_TRY(h, set_smem(stem2_kernel<float>, Stem2::SMEM));
+    CUDA_TRY(h, set_smem(stem2_kernel<__half>, Stem2::SMEM));
+    CUDA_TRY(h, set_smem(stem2_kernel<bf16>, Stem2::SMEM));
+    { const char* e = getenv("FVHD_STEM"); g_stem_gen = (e && e[0] == '1') ? 1 : 2; }
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
     { const char* e = getenv("FVHD_NO_SPLITK"); g_use_splitk = !(e && e[0] == '1'); }
     CUDA_TRY(h, cudaMalloc(&h->splitk_ws, kSplitKWsBytes));
@@ -451,6 +476,48 @@ int make_mixer_umma_step(fvhd_handle h, Step* st, const bf16* x, bf16* y, bf16* 
     const dim3 grid((unsigned)(per * mp.groups));
     *st = [=](cudaStream_t s, const RunCtx&) -> cudaError_t {
         return launch_k(repmixer_umma_kernel, grid, dim3(MixU::THREADS), MixU::SMEM, s, tm, mp);
+    };
+    return FVHD_OK;
+}
+
+// RepMixer depthwise pair with the 7x7 as Toeplitz products on tcgen05 (mixer_tz.cuh): one persistent CTA per SM, each bound to one
+// 8-channel group and walking that group's (image, 64 x 32 tile) items.
+int make_mixer_tz_step(fvhd_handle h, Step* st, const bf16* x, bf16* y, bf16* z, const float* w3, const float* b3, const float* w7,
+                       const float* b7, int batch, int H, int W, int C) {
+    if (C % MixZ::CG) return fail(h, FVHD_ERR_INVALID, "Toeplitz tcgen05 mixer needs C %% 8 == 0 (got %d)", C);
+    MixZParams mp{};
+    mp.y = y; mp.z = z; mp.w3 = w3; mp.b3 = b3; mp.w7 = w7; mp.b7 = b7;
+    mp.B = batch; mp.H = H; mp.W = W; mp.C = C;
+    mp.tiles_x = (W + MixZ::ZC - 1) / MixZ::ZC;
+    mp.tiles_y = (H + MixZ::ZR - 1) / MixZ::ZR;
+    mp.groups = C / MixZ::CG;
+    const int n_sp = batch * mp.tiles_x * mp.tiles_y;
+    // sibling clusters: FVHD_TZ_PAIR = cluster size (default 2; 1 = plain launch); must divide the number of channel groups
+    int cs = 2;
+    { const char* e = getenv("FVHD_TZ_PAIR"); if (e && e[0] >= '0' && e[0] <= '8') cs = e[0] - '0'; }
+    if (cs < 1) cs = 1;
+    while (cs > 1 && (mp.groups % cs || h->tz_clusters[cs] <= 0)) cs >>= 1;
+    mp.pair_sync = cs > 1 ? cs : 0;
+    int slots = cs > 1 ? h->tz_clusters[cs] * cs : h->num_sms;      // resident CTAs (one per SM; clusters are placed per GPC)
+    if (slots > h->num_sms) slots = h->num_sms;
+    int per = slots / mp.groups;
+    if (per < 1) per = 1;
+    if (per > n_sp) per = n_sp;
+    mp.ctas_per_group = per;
+    { const char* e = getenv("FVHD_TZ_SKIP"); mp.dbg = e ? atoi(e) : 0; }
+    int tz_pdl = 3;          // FVHD_TZ_PDL bits: 1 = launch with the programmatic-serialization attribute, 2 = trigger the successor early
+    { const char* e = getenv("FVHD_TZ_PDL"); if (e) tz_pdl = atoi(e); }
+    mp.pdl_trigger = (tz_pdl & 2) ? 1 : 0;
+    const bool attr = (tz_pdl & 1) != 0;
+    const int pair = cs;
+    CUtensorMap tm;
+    int rc = make_tmap_nhwc(h, &tm, x, batch, H, W, C, MixZ::XP, MixZ::XR, MixZ::CG);
+    if (rc != FVHD_OK) return rc;
+    CUtensorMap tmz;                                    // z store: one tile column (64 rows x 8 channels) per bulk copy
+    if ((rc = make_tmap_nhwc(h, &tmz, z, batch, H, W, C, 1, MixZ::ZR, MixZ::CG)) != FVHD_OK) return rc;
+    const dim3 grid((unsigned)(per * mp.groups));
+    *st = [=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+        return launch_kc(pair > 1 ? (attr ? pair : -pair) : (attr ? 1 : 0), repmixer_tz_kernel, grid, dim3(MixZ::THREADS), MixZ::SMEM, s, tm, tmz, mp);
     };
     return FVHD_OK;
 }
@@ -741,12 +808,23 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
             const int R = h->R, tiles = (R / 4 + STEM_TO - 1) / STEM_TO;
             const dim3 grid(tiles * tiles, 1, batch);
             bf16* t0 = bf.T1;
+            const double stem_flops = 2.0 * batch * ((double)(R / 2) * (R / 2) * 96 * 27 + (double)(R / 4) * (R / 4) * 96 * 9);
+            const double stem_bytes = (double)batch * (3.0 * R * R * 2 + (double)(R / 4) * (R / 4) * 96 * 2);
+            if (g_stem_gen == 2) {
+                const int n_tiles = tiles * tiles * batch;
+                const dim3 grid2((unsigned)std::min(n_tiles, 3 * h->num_sms));
+                pl.add([=](cudaStream_t s, const RunCtx& ctx) -> cudaError_t {
+                    if (ctx.img_dtype == FVHD_F32) return launch_k(stem2_kernel<float>, grid2, dim3(Stem2::THREADS), Stem2::SMEM, s, io, t0, w0, b0, w1, b1, R, tiles, n_tiles);
+                    if (ctx.img_dtype == FVHD_F16) return launch_k(stem2_kernel<__half>, grid2, dim3(Stem2::THREADS), Stem2::SMEM, s, io, t0, w0, b0, w1, b1, R, tiles, n_tiles);
+                    return launch_k(stem2_kernel<bf16>, grid2, dim3(Stem2::THREADS), Stem2::SMEM, s, io, t0, w0, b0, w1, b1, R, tiles, n_tiles);
+                }, "stem2_kernel", U, stem_flops, stem_bytes);
+            } else {
             pl.add([=](cudaStream_t s, const RunCtx& ctx) -> cudaError_t {
                 if (ctx.img_dtype == FVHD_F32) return launch_k(stem_kernel<float>, grid, dim3(STEM_THREADS), STEM_SMEM, s, io, t0, w0, b0, w1, b1, R, tiles);
                 if (ctx.img_dtype == FVHD_F16) return launch_k(stem_kernel<__half>, grid, dim3(STEM_THREADS), STEM_SMEM, s, io, t0, w0, b0, w1, b1, R, tiles);
                 return launch_k(stem_kernel<bf16>, grid, dim3(STEM_THREADS), STEM_SMEM, s, io, t0, w0, b0, w1, b1, R, tiles);
-            }, "stem_kernel", U, 2.0 * batch * ((double)(R / 2) * (R / 2) * 96 * 27 + (double)(R / 4) * (R / 4) * 96 * 9),
-               (double)batch * (3.0 * R * R * 2 + (double)(R / 4) * (R / 4) * 96 * 2));
+            }, "stem_kernel", U, stem_flops, stem_bytes);
+            }
             if ((rc = add_gemm(h, pl, U, t0, 96, WB(h, "stem.w2"), WF(h, "stem.b2"), nullptr, 0, out, 96, M, 96, 96, 1)) != FVHD_OK) return rc;
             in = nullptr;
             break;
@@ -770,6 +848,10 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
                 Step ms;
                 if ((rc = make_mixer_umma_step(h, &ms, in, bf.Y, bf.Z, w3, b3, w7, b7, batch, H, W, c)) != FVHD_OK) return rc;
                 pl.add(ms, "repmixer_umma_kernel", U, 2.0 * Md * c * 58, 3.0 * Md * c * 2);
+            } else if (g_mixer_mode == 'z' && !getenv("FVHD_MIX_TILE")) {
+                Step ms;
+                if ((rc = make_mixer_tz_step(h, &ms, in, bf.Y, bf.Z, w3, b3, w7, b7, batch, H, W, c)) != FVHD_OK) return rc;
+                pl.add(ms, "repmixer_tz_kernel", U, 2.0 * Md * c * 58, 3.0 * Md * c * 2);
             } else {
             bool small = false, wide = false, tc = g_mixer_mode != 'f';
             { const char* e = getenv("FVHD_MIX_TILE");
@@ -1536,6 +1618,23 @@ int fvhd_mixer(fvhd_handle h, void* stream, const void* x, const void* w3, const
         s = [=](cudaStream_t st, const RunCtx&) -> cudaError_t {
             return launch_k(repmixer_tc2_kernel, grid2, dim3(MixT2::NT), MixT2::SMEM, st, tm2, y2, z2, w3f, b3f, w7f, b7f, H, W, C, tx2);
         };
+    } else if (g_mixer_mode == 't') {   // FVHD_MIXER=t: the mma.sync-7x7 kernel of mixer_tc.cuh (32-channel groups)
+        if (C % DW_CG) return fail(h, FVHD_ERR_INVALID, "fvhd_mixer: C %% 32 != 0");
+        const int tx = (W + 15) / 16, ty = (H + 15) / 16;
+        int per_group = (2 * h->num_sms) / (C / DW_CG);
+        if (per_group < 1) per_group = 1;
+        if (per_group > tx * ty * batch) per_group = tx * ty * batch;
+        const dim3 grid_tc(per_group, C / DW_CG, 1);
+        CUtensorMap tmx;
+        if ((rc = make_tmap_nhwc(h, &tmx, x, batch, H, W, C, MixTc::XP, MixTc::XH)) != FVHD_OK) return rc;
+        bf16 *y2 = (bf16*)y, *z2 = (bf16*)z;
+        const float *w3f = (const float*)w3, *b3f = (const float*)b3, *w7f = (const float*)w7, *b7f = (const float*)b7;
+        s = [=](cudaStream_t st, const RunCtx&) -> cudaError_t {
+            return launch_k(repmixer_tc_kernel, grid_tc, dim3(MixTc::NT), MixTc::SMEM, st, tmx, y2, z2, w3f, b3f, w7f, b7f, H, W, C, tx, batch);
+        };
+    } else if (g_mixer_mode == 'z') {   // FVHD_MIXER=z: Toeplitz tcgen05 kernel (mixer_tz.cuh)
+        if ((rc = make_mixer_tz_step(h, &s, (const bf16*)x, (bf16*)y, (bf16*)z, (const float*)w3, (const float*)b3, (const float*)w7,
+                                     (const float*)b7, batch, H, W, C)) != FVHD_OK) return rc;
     } else if ((rc = make_mixer_umma_step(h, &s, (const bf16*)x, (bf16*)y, (bf16*)z, (const float*)w3, (const float*)b3, (const float*)w7,
                                    (const float*)b7, batch, H, W, C)) != FVHD_OK) return rc;
     RunCtx ctx{};

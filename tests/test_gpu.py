@@ -166,22 +166,23 @@ def _engine_with_env(R, packed, dev, env):
 
 
 def test_mixer_variants_agree(packed, oracle256, dev):
-    """RepMixer depthwise pair: tcgen05 diagonal-tap mixer (mixer_umma.cuh, FVHD_MIXER=u) vs the mma.sync-7x7 kernel (default) vs the FMA-pipe
+    """RepMixer depthwise pair: tcgen05 diagonal-tap mixer (mixer_umma.cuh, FVHD_MIXER=u) vs the mma.sync-7x7 kernel (FVHD_MIXER=t) vs the Toeplitz tcgen05 kernel (default) vs the FMA-pipe
     kernel (FVHD_MIX_TILE=a): same oracle inputs, each block in isolation, including ragged maps smaller than a tile."""
     ref, col = oracle256
-    um, tc, fma = (_engine_with_env(256, packed, dev, e) for e in ({"FVHD_MIXER": "u"}, {}, {"FVHD_MIX_TILE": "a"}))
+    um, tc, fma, tz = (_engine_with_env(256, packed, dev, e) for e in ({"FVHD_MIXER": "u"}, {"FVHD_MIXER": "t"}, {"FVHD_MIX_TILE": "a"}, {}))
     kern = lambda e: {s["kernel"] for s in e.steps(1)}
     assert "repmixer_umma_kernel" in kern(um) and "repmixer_tc_kernel" in kern(tc) and "repmixer_dw_kernel" in kern(fma)
+    assert "repmixer_tz_kernel" in kern(tz)               # the default: Toeplitz tcgen05 mixer (mixer_tz.cuh)
     prev, worst = None, 0.0
     for u in um.units():
         name = u["name"]
         if prev is not None and any(s["unit"] == u["index"] and s["kernel"] == "repmixer_umma_kernel" for s in um.steps(1)):
             xin = _nhwc(prev, dev)
-            outs = [e.run_units(u["index"], u["index"], xin, 1) for e in (um, tc, fma)]
+            outs = [e.run_units(u["index"], u["index"], xin, 1) for e in (um, tc, fma, tz)]
             want = col[name].permute(0, 2, 3, 1).reshape(-1)
             for o in outs:
                 assert rel_l2(o.float().reshape(-1), want) < UNIT_TOL, name
-            worst = max(worst, rel_l2(outs[0], outs[1]), rel_l2(outs[0], outs[2]))
+            worst = max(worst, rel_l2(outs[0], outs[1]), rel_l2(outs[0], outs[2]), rel_l2(outs[0], outs[3]))
         prev = col.get(name)
     assert 0.0 < worst < 8e-3, worst          # different rounding inside the block (bf16 taps / f16 y / bf16 y), nothing more
     # ragged tiles: at 128 px stage 1 is 16x16, stage 2 is 8x8 -- smaller than any tile; random activations

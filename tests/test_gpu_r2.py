@@ -235,9 +235,10 @@ def _mixer_ref(x_nhwc, w3, b3, w7, b7, round_weights):
     (3, 40, 24, 32),       # ragged in both directions, 2 channel groups, batch 3
     (1, 96, 96, 48),       # 1536-px geometry (3 tiles across), 3 groups
 ])
-@pytest.mark.parametrize("mode", ["u", "2"])
+@pytest.mark.parametrize("mode", ["z", "u", "2"])
 def test_umma_mixer_vs_torch(dev, B, H, W, C, mode):
-    """mode u: tcgen05 diagonal-tap kernel (mixer_umma.cuh, bf16 taps); mode 2: both convs on mma.sync (mixer_tc2.cuh, f16 taps)."""
+    """mode z: Toeplitz tcgen05 kernel (mixer_tz.cuh, bf16 planes and taps); mode u: tcgen05 diagonal-tap kernel (mixer_umma.cuh, bf16
+    taps); mode 2: both convs on mma.sync (mixer_tc2.cuh, f16 taps)."""
     os.environ["FVHD_MIXER"] = mode                      # read when a handle first touches CUDA
     try:
         eng = pkg.Engine(64, 0, 2, 1)
@@ -253,6 +254,8 @@ def test_umma_mixer_vs_torch(dev, B, H, W, C, mode):
     y, z = eng.mixer(x.to(dev), w3.to(dev), b3.to(dev), w7.to(dev), b7.to(dev))
     torch.cuda.synchronize()
     yr, zr = _mixer_ref(x, w3, b3, w7, b7, round_weights=(mode == "u"))   # mode u rounds the taps to bf16; mode 2 to f16 (~exact)
+    if mode == "z":                                     # mode z: fp32 3x3 taps (FMA pipes), bf16 7x7 taps (Toeplitz tiles)
+        yr, zr = _mixer_ref(x, w3, b3, w7.to(torch.bfloat16).float(), b7, round_weights=False)
     ye, ze = _mixer_ref(x, w3, b3, w7, b7, round_weights=False)      # exact fp32 taps (what the oracle computes)
     ey, ez = rel_l2(y.float(), yr), rel_l2(z.float(), zr)
     print(f"mixer[{mode}] {B}x{H}x{W}x{C}: y {ey:.2e} z {ez:.2e} | vs fp32 taps: y {rel_l2(y.float(), ye):.2e} z {rel_l2(z.float(), ze):.2e}")
@@ -261,7 +264,7 @@ def test_umma_mixer_vs_torch(dev, B, H, W, C, mode):
     assert rel_l2(y.float(), ye) < 5e-3 and rel_l2(z.float(), ze) < 6e-3
 
 
-@pytest.mark.parametrize("mode", ["u", "2"])
+@pytest.mark.parametrize("mode", ["z", "u", "2"])
 def test_umma_mixer_identity_taps(dev, mode):
     """Centre taps = 1, everything else 0: y == x + b3, z == y + b7 exactly (bf16 in, fp32 accumulate, bf16 out)."""
     os.environ["FVHD_MIXER"] = mode
@@ -277,7 +280,7 @@ def test_umma_mixer_identity_taps(dev, mode):
     w7 = torch.zeros(49, C); w7[24] = 1.0
     zb = torch.zeros(C)
     y, z = eng.mixer(x.to(dev), w3.to(dev), zb.to(dev), w7.to(dev), zb.to(dev))
-    if mode == "u":
+    if mode in ("u", "z"):
         assert torch.equal(y.cpu(), x) and torch.equal(z.cpu(), x)
     else:       # f16 planes: bf16 values below 2^-14 land on the f16 subnormal grid (quantum 2^-24); everything else is exact
         assert (y.float().cpu() - x.float()).abs().max().item() <= 2 ** -24 and (z.float().cpu() - x.float()).abs().max().item() <= 2 ** -23
@@ -432,3 +435,75 @@ def test_repmixer_block_large_activations(packed, tower_sd, dev):
                 err = rel_l2(got, want)
                 print(f"{name} x{scale:g}: rel-L2 {err:.2e}")
                 assert err < 8e-3, (name, scale, err)
+
+
+# ------------------------------------------------------------------ plan variants: Toeplitz tcgen05 mixer, stem generations
+def _engine_env(R, packed, dev, env, batch=1):
+    """Engine whose plan is built under the given FVHD_* switches (read when a handle first touches CUDA / builds its plan)."""
+    keys = ("FVHD_MIX_TILE", "FVHD_MIXER", "FVHD_STEM")
+    old = {k: os.environ.pop(k, None) for k in keys}
+    os.environ.update(env)
+    try:
+        eng = pkg.Engine(R, 896, 2, batch).load(packed, dev)
+        eng.forward(fx.synthetic_images(batch, R).to(dev), False, True)
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+            if old[k] is not None:
+                os.environ[k] = old[k]
+    return eng
+
+
+def test_tz_mixer_units_vs_oracle_1024(packed, oracle1024_b3, dev):
+    """Every RepMixer block through the Toeplitz tcgen05 mixer (mixer_tz.cuh, FVHD_MIXER=z) at 1024 px, batch 3, fed the oracle's inputs."""
+    x, ref, col = oracle1024_b3
+    B = x.shape[0]
+    eng = _engine_env(1024, packed, dev, {"FVHD_MIXER": "z"}, batch=B)
+    steps = eng.steps(B)
+    assert any(s["kernel"] == "repmixer_tz_kernel" for s in steps)
+    prev, worst, n = None, 0.0, 0
+    for u in eng.units():
+        name = u["name"]
+        if prev is not None and any(s["unit"] == u["index"] and s["kernel"] == "repmixer_tz_kernel" for s in steps):
+            got = eng.run_units(u["index"], u["index"], _nhwc(prev, dev), B)
+            assert torch.isfinite(got.float()).all(), name
+            worst = max(worst, rel_l2(got.float().reshape(-1), col[name].permute(0, 2, 3, 1).reshape(-1)))
+            n += 1
+        prev = col.get(name)
+    print(f"tz mixer blocks: {n}, worst unit error {worst:.2e}")
+    assert n == 38 and worst < UNIT_TOL_1024, (n, worst)
+
+
+def test_tz_mixer_end_to_end_256_and_ragged(packed, tower_sd, proj_sd, dev):
+    """encode_images with FVHD_MIXER=z at 256 px (maps smaller than the 64 x 32 tile in stage 2) vs the oracle, and == itself on a rerun."""
+    x = fx.synthetic_images(2, 256, seed=7)
+    ref = orc.encode_images(x, tower_sd, proj_sd)
+    eng = _engine_env(256, packed, dev, {"FVHD_MIXER": "z"}, batch=2)
+    _, p1 = eng.forward(x.to(dev), False, True)
+    _, p2 = eng.forward(x.to(dev), False, True)
+    torch.cuda.synchronize()
+    assert torch.equal(p1, p2)
+    assert rel_l2(p1.float(), ref) < E2E_TOL
+
+
+@pytest.mark.parametrize("R,B", [(256, 2), (1024, 1)])
+def test_stem_generations_agree(packed, tower_sd, proj_sd, dev, R, B):
+    """stem2_kernel (default: persistent, packed-half GELUs) and the first-generation stem_kernel (FVHD_STEM=1) against the oracle's stem."""
+    x = fx.synthetic_images(B, R, seed=11)
+    col = {}
+    want = orc.convolutional_stem(x, tower_sd).permute(0, 2, 3, 1).reshape(-1)
+    outs = {}
+    for gen in ("2", "1"):
+        eng = _engine_env(R, packed, dev, {"FVHD_STEM": gen}, batch=B)
+        names = {s["kernel"] for s in eng.steps(B)}
+        assert ("stem2_kernel" in names) == (gen == "2") and ("stem_kernel" in names) == (gen == "1")
+        u = eng.units()[0]
+        assert u["name"] == "stem"
+        for dt in (torch.bfloat16, torch.float16, torch.float32):
+            got = eng.run_units(0, 0, x.to(dev).to(dt), B)
+            e = rel_l2(got.float().reshape(-1), want)
+            assert torch.isfinite(got.float()).all() and e < UNIT_TOL_1024, (gen, dt, e)
+        outs[gen] = eng.run_units(0, 0, x.to(dev).to(torch.bfloat16), B)
+    d = rel_l2(outs["2"].float(), outs["1"].float())
+    print(f"stem R={R}: gen2 vs gen1 {d:.2e}")
+    assert d < 6e-3
