@@ -14,6 +14,14 @@
 //   * C = 384 in ONE CTA: acc2 = 384 TMEM columns as two N = 192 halves, half-chunk weight slots (as the cluster kernel),
 //     three 24-KB slots -- this is the large-batch path of stage 2 (two plain GEMMs and a 12.6-MB hidden per image before);
 //   * results leave through 16-B global stores straight from registers (no staging buffer: the smem goes to z / W).
+//   * CS = 2 (optional, FVHD_CONVFFN_CS): launched as 2-CTA clusters that SHARE THE WEIGHT STREAM.  The two CTAs of a cluster work on
+//     neighbouring tiles and walk the same ring of weight slots; every slot is fetched ONCE per cluster -- even slots by rank 0, odd
+//     slots by rank 1 -- as a TMA multicast into both CTAs' rings (each CTA arms its own full barrier; a slot is reused when BOTH MMA
+//     warps have released it: tcgen05.commit multicast onto both empty barriers).  Per-SM weight ingest halves; results are
+//     bit-identical.  Measured neutral at batch 32 (the kernel is bound by its MMA1 -> GELU -> MMA2 chain there, not by ingest).
+// Two restructurings were also measured at batch 32 and NOT kept (profiles/r02_findings.md): MMA1 running ahead of MMA2 across tile
+// boundaries with the accumulator drain on 8 dedicated warps (C = 192: 415 vs 383 us per launch), and the 16 GELU warps split into
+// two groups alternating over the chunks (412 us).
 #pragma once
 #include "mlp_fused.cuh"
 
@@ -73,10 +81,11 @@ __device__ __forceinline__ uint32_t gelu_f16x2(float a, float b) {
     return r;
 }
 
-template <int C>
+template <int C, int CS = 1>
 __global__ void __launch_bounds__(CF_THREADS, 1)
 convffn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW1,
                        const __grid_constant__ CUtensorMap tmW2, const MlpParams p) {
+    static_assert(CS == 1 || CS == 2, "cluster size");
     using Cfg = CfCfg<C>;
     constexpr int KB = Cfg::KB, NC = Cfg::NC, NSLOT = Cfg::NSLOT, W1U = Cfg::W1U, W2U = Cfg::W2U, N2 = Cfg::N2, KB1 = Cfg::KB1;
     constexpr int NB = Cfg::NB, LA = NB - 1, ACC1 = Cfg::ACC1_COL;
@@ -104,11 +113,18 @@ convffn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
     pdl_launch_dependents();
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // broadcast: role branches are warp-uniform for ptxas
     const int lane = threadIdx.x & 31;
+    // tile walk: cluster `cl` of `ncl` takes tiles CS * (cl + k * ncl) + rank, k = 0, 1, ...; every CTA of a cluster runs the same
+    // number of iterations (with CS = 2 and an odd tile count the last tile index of rank 1 is tiles_m: its z box is out of bounds
+    // = zeros, its rows fail row_ok, nothing is stored), so the shared weight stream never loses a consumer
+    const int rank = CS == 1 ? 0 : (int)(blockIdx.x % CS);
+    const int cl = (int)blockIdx.x / CS, ncl = (int)gridDim.x / CS;
+    const int tile0 = CS * cl + rank, tstep = CS * ncl;
+    const int tile_end = p.tiles_m + rank;         // tile < tile_end  <=>  CS * (cl + k * ncl) < tiles_m
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
         mbar_init(z_full, 1); mbar_init(z_empty, 1);
-        for (int s = 0; s < NSLOT; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (int s = 0; s < NSLOT; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], CS); }
         for (int b = 0; b < NB; ++b) {
             mbar_init(&a1_full[b], 1); mbar_init(&a1_empty[b], CF_EPI_WARPS);
             mbar_init(&h_full[b], CF_EPI_WARPS); mbar_init(&h_empty[b], 1);
@@ -126,6 +142,7 @@ convffn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (CS > 1) cluster_sync_all();              // the sibling's barriers exist before anything is multicast or committed onto them
 
     if (warp == 0) {
         if (lane == 0) {
@@ -134,15 +151,23 @@ convffn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
             auto load_w = [&](bool is_w2, int j, int u) {
                 const int s = wit % NSLOT;
                 const uint32_t ph = (uint32_t)(wit / NSLOT) & 1u;
+                const bool mine = CS == 1 || (wit & (CS - 1)) == rank;           // CS = 2: this slot-load is fetched by one CTA for both
                 ++wit;
-                mbar_wait(&w_empty[s], ph ^ 1u);
+                mbar_wait(&w_empty[s], ph ^ 1u);                                 // (CS = 2: released by BOTH MMA warps)
                 uint8_t* dst = smemW + (size_t)s * CF_SLOT;
                 if (!is_w2) {           // W1 rows [64 j, +64), k-blocks [KB1 u, +KB1): KB1 boxes of 64 x 64
                     mbar_expect_tx(&w_full[s], (uint32_t)KB1 * 64 * 128);
-                    for (int kk = 0; kk < KB1; ++kk) tma_load_2d(dst + (size_t)kk * 64 * 128, &tmW1, (KB1 * u + kk) * 64, j * MLP_NH, &w_full[s]);
+                    if (mine)
+                        for (int kk = 0; kk < KB1; ++kk) {
+                            if (CS == 1) tma_load_2d(dst + (size_t)kk * 64 * 128, &tmW1, (KB1 * u + kk) * 64, j * MLP_NH, &w_full[s]);
+                            else tma_load_2d_mc(dst + (size_t)kk * 64 * 128, &tmW1, (KB1 * u + kk) * 64, j * MLP_NH, &w_full[s], (uint16_t)((1u << CS) - 1u));
+                        }
                 } else {                // W2 rows [N2 u, +N2), K columns [64 j, +64): one N2 x 64 box
                     mbar_expect_tx(&w_full[s], (uint32_t)N2 * 128);
-                    tma_load_2d(dst, &tmW2, j * MLP_NH, u * N2, &w_full[s]);
+                    if (mine) {
+                        if (CS == 1) tma_load_2d(dst, &tmW2, j * MLP_NH, u * N2, &w_full[s]);
+                        else tma_load_2d_mc(dst, &tmW2, j * MLP_NH, u * N2, &w_full[s], (uint16_t)((1u << CS) - 1u));
+                    }
                 }
             };
             // a tile's weight stream in the MMA warp's consumption order: step t issues W1[t] (t < NC) then W2[t - LA] (t >= LA);
@@ -158,10 +183,10 @@ convffn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
                 }
             };
             int q0 = 0;                                  // weights are constants: first ring fill before the PDL wait
-            if ((int)blockIdx.x < p.tiles_m) { q0 = NSLOT < TOT ? NSLOT : TOT; run_tile_loads(0, q0); }
+            if (tile0 < tile_end) { q0 = NSLOT < TOT ? NSLOT : TOT; run_tile_loads(0, q0); }
             pdl_wait();
             int ti = 0;
-            for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x, ++ti) {
+            for (int tile = tile0; tile < tile_end; tile += tstep, ++ti) {
                 mbar_wait(z_empty, ((uint32_t)ti & 1u) ^ 1u);
                 mbar_expect_tx(z_full, (uint32_t)Cfg::Z_BYTES);
                 for (int kb = 0; kb < KB; ++kb) tma_load_2d(smemZ + (size_t)kb * GEMM_A_STAGE_BYTES, &tmZ, kb * 64, tile * GEMM_BM, z_full);
@@ -184,7 +209,7 @@ convffn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
             mbar_wait(&w_full[s], ph);
             return s;
         };
-        for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x, ++ti) {
+        for (int tile = tile0; tile < tile_end; tile += tstep, ++ti) {
             mbar_wait(z_full, (uint32_t)ti & 1u);
 #pragma unroll 1
             for (int t = 0; t < NC + LA; ++t) {
@@ -208,7 +233,7 @@ convffn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
                                               (u | kk | k) != 0 ? 1u : 0u);
                             }
                         }
-                        if (elect_one()) umma_commit(&w_empty[s]);
+                        if (elect_one()) { if (CS == 1) umma_commit(&w_empty[s]); else umma_commit_mc(&w_empty[s], (uint16_t)((1u << CS) - 1u)); }
                         __syncwarp();
                     }
                     if (elect_one()) {
@@ -231,7 +256,7 @@ convffn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             if (elect_one()) umma_bf16(tm + (uint32_t)(u * N2), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (j | k) != 0 ? 1u : 0u);
-                        if (elect_one()) umma_commit(&w_empty[s]);
+                        if (elect_one()) { if (CS == 1) umma_commit(&w_empty[s]); else umma_commit_mc(&w_empty[s], (uint16_t)((1u << CS) - 1u)); }
                         __syncwarp();
                     }
                     if (elect_one()) umma_commit(&h_empty[b]);
@@ -251,7 +276,7 @@ convffn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         pdl_wait();
         int ti = 0;
-        for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x, ++ti) {
+        for (int tile = tile0; tile < tile_end; tile += tstep, ++ti) {
             const int row = tile * GEMM_BM + row_in_tile;
             const bool row_ok = row < p.M;
             // ---- epilogue 1 per hidden chunk: columns [16 k4, +16) of the 64-wide chunk -> GELU -> f16 -> H[b]
@@ -326,6 +351,7 @@ convffn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+    if (CS > 1) cluster_sync_all();              // no CTA exits while its sibling may still multicast into its ring / commit onto its barriers
 }
 
 }  // namespace fvhd

@@ -89,6 +89,7 @@ struct fvhd_handle_s {
     size_t ws_bytes = 0;
     EncodeTiledFn encode = nullptr;
     int num_sms = 148;
+    int cf_clusters[3] = {0, 0, 0};   // resident 2-CTA clusters of convffn_tcgen05_kernel<C, 2>, C = 96 / 192 / 384
     int tz_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // [cs]: resident cs-CTA clusters of repmixer_tz_kernel (cs = 2, 4, 8)
     int mlpc_clusters = 0;        // resident 4-CTA clusters of mlp_cluster_tcgen05_kernel (cudaOccupancyMaxActiveClusters)
     bool use_graph = true;
@@ -387,9 +388,31 @@ int ensure_cuda(fvhd_handle h) {
     { const char* e = getenv("FVHD_ATTN"); g_attn_mode = (e && e[0]) ? e[0] : g_attn_default; }
     CUDA_TRY(h, set_smem(attention_umma_kernel, AttU::SMEM));
     { const char* e = getenv("FVHD_CONVFFN"); g_convffn_gen = (e && e[0] == '2') ? 2 : (e && e[0] == '1') ? 1 : g_convffn_default; }
-    CUDA_TRY(h, set_smem(convffn_tcgen05_kernel<96>, CfCfg<96>::SMEM));
-    CUDA_TRY(h, set_smem(convffn_tcgen05_kernel<192>, CfCfg<192>::SMEM));
-    CUDA_TRY(h, set_smem(convffn_tcgen05_kernel<384>, CfCfg<384>::SMEM));
+    CUDA_TRY(h, (set_smem(convffn_tcgen05_kernel<96, 1>, CfCfg<96>::SMEM)));
+    CUDA_TRY(h, (set_smem(convffn_tcgen05_kernel<192, 1>, CfCfg<192>::SMEM)));
+    CUDA_TRY(h, (set_smem(convffn_tcgen05_kernel<384, 1>, CfCfg<384>::SMEM)));
+    CUDA_TRY(h, (set_smem(convffn_tcgen05_kernel<96, 2>, CfCfg<96>::SMEM)));
+    CUDA_TRY(h, (set_smem(convffn_tcgen05_kernel<192, 2>, CfCfg<192>::SMEM)));
+    CUDA_TRY(h, (set_smem(convffn_tcgen05_kernel<384, 2>, CfCfg<384>::SMEM)));
+    {   // resident 2-CTA clusters of the weight-sharing ConvFFN variant, per C
+        const size_t sm[3] = {CfCfg<96>::SMEM, CfCfg<192>::SMEM, CfCfg<384>::SMEM};
+        for (int ci = 0; ci < 3; ++ci) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(prop.multiProcessorCount / 2 * 2));
+            cfg.blockDim = dim3(CF_THREADS);
+            cfg.dynamicSmemBytes = sm[ci];
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int nc = 0;
+            cudaError_t e = ci == 0 ? cudaOccupancyMaxActiveClusters(&nc, convffn_tcgen05_kernel<96, 2>, &cfg)
+                          : ci == 1 ? cudaOccupancyMaxActiveClusters(&nc, convffn_tcgen05_kernel<192, 2>, &cfg)
+                                    : cudaOccupancyMaxActiveClusters(&nc, convffn_tcgen05_kernel<384, 2>, &cfg);
+            if (e != cudaSuccess) { nc = 0; (void)cudaGetLastError(); }
+            h->cf_clusters[ci] = nc;
+        }
+    }
     CUDA_TRY(h, set_smem(dwconv_kernel<7, 1, 1, 0, 16, 16, 8>, DwCfg<7, 1, 1, 16, 16>::SMEM));
     CUDA_TRY(h, set_smem(dwconv_kernel<7, 2, 2, 1, 8, 8, 4>, DwCfg<7, 2, 2, 8, 8>::SMEM));
     CUDA_TRY(h, set_smem(dwconv_kernel<3, 1, 2, 0, 16, 16, 8>, DwCfg<3, 1, 2, 16, 16>::SMEM));
@@ -730,10 +753,25 @@ int make_convffn2_step_t(fvhd_handle h, Step* st, const bf16* z, const bf16* w1,
     if ((rc = make_tmap(h, &tz, z, M, C, C, GEMM_BM)) != FVHD_OK) return rc;
     if ((rc = make_tmap(h, &tw1, w1, 4 * C, C, C, MLP_NH)) != FVHD_OK) return rc;
     if ((rc = make_tmap(h, &tw2, w2, C, 4 * C, 4 * C, CfCfg<C>::N2)) != FVHD_OK) return rc;
-    const dim3 grid((unsigned)(mp.tiles_m < h->num_sms ? mp.tiles_m : h->num_sms));
     const size_t smem = CfCfg<C>::SMEM;
+    // FVHD_CONVFFN_CS=2: 2-CTA clusters sharing the weight stream by TMA multicast (halves each SM's L2 -> smem weight ingest).
+    // Bit-identical and tested, but measured NEUTRAL at batch 32 (C = 384: 303.5 vs 304.0 us, C = 192: 383.7 vs 386.4 us per launch):
+    // the kernel is bound by its MMA1 -> GELU -> MMA2 dependency chain, not by operand ingest.  Default: single CTAs.
+    int cs = 1;
+    { const char* e = getenv("FVHD_CONVFFN_CS"); if (e && (e[0] == '1' || e[0] == '2')) cs = e[0] - '0'; }
+    const int ci = C == 96 ? 0 : C == 192 ? 1 : 2;
+    if (cs == 2 && h->cf_clusters[ci] <= 0) cs = 1;
+    if (cs == 2) {
+        const int want = (mp.tiles_m + 1) / 2;
+        const dim3 grid2((unsigned)(2 * (want < h->cf_clusters[ci] ? want : h->cf_clusters[ci])));
+        *st = [=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+            return launch_kc(2, convffn_tcgen05_kernel<C, 2>, grid2, dim3(CF_THREADS), smem, s, tz, tw1, tw2, mp);
+        };
+        return FVHD_OK;
+    }
+    const dim3 grid((unsigned)(mp.tiles_m < h->num_sms ? mp.tiles_m : h->num_sms));
     *st = [=](cudaStream_t s, const RunCtx&) -> cudaError_t {
-        return launch_k(convffn_tcgen05_kernel<C>, grid, dim3(CF_THREADS), smem, s, tz, tw1, tw2, mp);
+        return launch_k(convffn_tcgen05_kernel<C, 1>, grid, dim3(CF_THREADS), smem, s, tz, tw1, tw2, mp);
     };
     return FVHD_OK;
 }
@@ -848,7 +886,12 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
                 Step ms;
                 if ((rc = make_mixer_umma_step(h, &ms, in, bf.Y, bf.Z, w3, b3, w7, b7, batch, H, W, c)) != FVHD_OK) return rc;
                 pl.add(ms, "repmixer_umma_kernel", U, 2.0 * Md * c * 58, 3.0 * Md * c * 2);
-            } else if (g_mixer_mode == 'z' && !getenv("FVHD_MIX_TILE")) {
+            } else if (g_mixer_mode == 'z' && !getenv("FVHD_MIX_TILE") &&
+                       ((long)batch * ((W + MixZ::ZC - 1) / MixZ::ZC) * ((H + MixZ::ZR - 1) / MixZ::ZR) * (c / MixZ::CG) >= h->num_sms || c % DW_CG != 0 ||
+                        getenv("FVHD_MIXER") != nullptr)) {
+                // Toeplitz tcgen05 mixer whenever there is at least one 64 x 32 x 8 item per SM; below that (stage 2 of a single
+                // 1024-px image: 96 items) the finer-grained mma.sync kernel of mixer_tc.cuh has the shorter critical path
+                // (16 vs 20 us per launch at batch 1).  An explicit FVHD_MIXER=z forces it everywhere.
                 Step ms;
                 if ((rc = make_mixer_tz_step(h, &ms, in, bf.Y, bf.Z, w3, b3, w7, b7, batch, H, W, c)) != FVHD_OK) return rc;
                 pl.add(ms, "repmixer_tz_kernel", U, 2.0 * Md * c * 58, 3.0 * Md * c * 2);

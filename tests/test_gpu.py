@@ -169,10 +169,10 @@ def test_mixer_variants_agree(packed, oracle256, dev):
     """RepMixer depthwise pair: tcgen05 diagonal-tap mixer (mixer_umma.cuh, FVHD_MIXER=u) vs the mma.sync-7x7 kernel (FVHD_MIXER=t) vs the Toeplitz tcgen05 kernel (default) vs the FMA-pipe
     kernel (FVHD_MIX_TILE=a): same oracle inputs, each block in isolation, including ragged maps smaller than a tile."""
     ref, col = oracle256
-    um, tc, fma, tz = (_engine_with_env(256, packed, dev, e) for e in ({"FVHD_MIXER": "u"}, {"FVHD_MIXER": "t"}, {"FVHD_MIX_TILE": "a"}, {}))
+    um, tc, fma, tz = (_engine_with_env(256, packed, dev, e) for e in ({"FVHD_MIXER": "u"}, {"FVHD_MIXER": "t"}, {"FVHD_MIX_TILE": "a"}, {"FVHD_MIXER": "z"}))
     kern = lambda e: {s["kernel"] for s in e.steps(1)}
     assert "repmixer_umma_kernel" in kern(um) and "repmixer_tc_kernel" in kern(tc) and "repmixer_dw_kernel" in kern(fma)
-    assert "repmixer_tz_kernel" in kern(tz)               # the default: Toeplitz tcgen05 mixer (mixer_tz.cuh)
+    assert "repmixer_tz_kernel" in kern(tz)               # Toeplitz tcgen05 mixer (mixer_tz.cuh): the default wherever a launch has >= 1 item per SM
     prev, worst = None, 0.0
     for u in um.units():
         name = u["name"]

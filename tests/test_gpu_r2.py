@@ -507,3 +507,40 @@ def test_stem_generations_agree(packed, tower_sd, proj_sd, dev, R, B):
     d = rel_l2(outs["2"].float(), outs["1"].float())
     print(f"stem R={R}: gen2 vs gen1 {d:.2e}")
     assert d < 6e-3
+
+
+# ------------------------------------------------------------------ fused ConvFFN, 2-CTA clusters sharing the weight stream
+@pytest.mark.parametrize("C,M", [(96, 70000), (192, 9000), (192, 128), (384, 4096), (384, 9000), (384, 40000)])
+def test_convffn2_weight_sharing_clusters_bit_identical(dev, C, M):
+    """convffn_tcgen05_kernel<C, 2> (TMA-multicast weight ring shared by two CTAs; odd tile counts leave rank 1 one dummy tile) must
+    reproduce the single-CTA kernel bit for bit: same MMAs in the same order, only the origin of the weight bytes differs."""
+    eng = pkg.Engine(64, 0, 2, 1)
+    g = torch.Generator().manual_seed(3 * C + M)
+    z = torch.randn(M, C, generator=g).to(torch.bfloat16).to(dev)
+    w1 = (torch.randn(4 * C, C, generator=g) / C ** 0.5).to(torch.bfloat16).to(dev)
+    w2h = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).to(torch.float16).to(dev)
+    b1 = torch.randn(4 * C, generator=g).to(dev)
+    b2 = torch.randn(C, generator=g).to(dev)
+    r = torch.randn(M, C, generator=g).to(torch.bfloat16).to(dev)
+    outs = {}
+    for cs in ("1", "2"):
+        os.environ["FVHD_CONVFFN_CS"] = cs
+        try:
+            outs[cs] = [eng.convffn2(z, w1, b1, w2h, b2, r) for _ in range(3)]
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("FVHD_CONVFFN_CS", None)
+    ref = r.float() + torch.nn.functional.gelu(z.float() @ w1.float().t() + b1) .to(torch.float16).float() @ w2h.float().t() + b2
+    assert rel_l2(outs["1"][0].float(), ref) < 6e-3
+    for o in outs["2"]:
+        assert torch.equal(o, outs["1"][0])
+
+
+def test_default_plan_picks_mixer_per_launch(packed, dev):
+    """Default plan at 1024 px: the Toeplitz tcgen05 mixer where a launch has at least one 64 x 32 x 8 item per SM (stages 0-1 at batch 1,
+    every stage at batch 4), the finer-grained mma.sync mixer below that (stage 2 of a single image: 96 items)."""
+    eng = _engine_env(1024, packed, dev, {}, batch=4)
+    k1 = [s["kernel"] for s in eng.steps(1)]
+    k4 = [s["kernel"] for s in eng.steps(4)]
+    assert k1.count("repmixer_tz_kernel") == 14 and k1.count("repmixer_tc_kernel") == 24, (k1.count("repmixer_tz_kernel"), k1.count("repmixer_tc_kernel"))
+    assert k4.count("repmixer_tz_kernel") == 38 and "repmixer_tc_kernel" not in k4
