@@ -22,8 +22,8 @@ Multi-GPU: images shard by batch, one process per GPU (weak scaling for the head
              (strong scaling) without any collective, with the all-gather FUSED into the projector epilogue (peer stores over
              NVLink into symmetric memory) and with a separate NCCL all-gather pass; tcgen05 roofline fraction at that batch.
   ttft       BASELINE.json configs[2] (and configs[4] with --ttft7b / at N=8): p50 time to first token, uint8 host image ->
-             GPU preprocessing -> encode_images (splice store) -> stock-HF Qwen2 prefill -> first token; every rank runs its
-             own replica (a single image is not sharded: flat in N by design).
+             GPU preprocessing -> encode_images (splice store) -> Qwen2 prefill on the library (row f3) -> first token, with the
+             stock-HF prefill timed next to it; every rank runs its own replica (a single image is not sharded: flat in N by design).
   sustained  >= 2 s of back-to-back forwards with the clock sampler running (the 50-step timed region is ~0.1 s).
 """
 import argparse
@@ -284,7 +284,10 @@ def gpu_eager_baseline(dev, batches=(1, 32)):
 
 
 def ttft_run(dev, res, hidden, llm_shape, runs, warmup, pkg, fx):
-    """p50 TTFT of one replica on `dev` (see tools/ttft.py for the definition; FastVLMModel.swift:114-138, predict.py:51-65)."""
+    """p50 TTFT of one replica on `dev` (see tools/ttft.py for the definition; FastVLMModel.swift:114-138, predict.py:51-65):
+    uint8 host image -> H2D -> GPU preprocessing -> encode_images (projector epilogue stores at the <image> position of the LLM's input
+    sequence) -> text embeddings -> LLM prefill -> first token on the host.  The prefill runs on the library (row f3, LlmPrefill: tcgen05
+    GEMMs + llm.cuh, one CUDA graph); the same flow with the stock Hugging Face prefill is timed next to it (`hf_prefill`)."""
     import numpy as np
     import torch
     from transformers import Qwen2Config, Qwen2ForCausalLM
@@ -300,33 +303,63 @@ def ttft_run(dev, res, hidden, llm_shape, runs, warmup, pkg, fx):
     host_u8 = torch.from_numpy(np.random.default_rng(0).integers(0, 256, (res, res, 3), dtype=np.uint8)).pin_memory()
     img = torch.empty(1, 3, res, res, dtype=torch.float16, device=dev)
     n_pre, n_post = 14, 17                       # qwen_2 template around "<image>\nDescribe the image." (predict.py:34-42,80)
+    seq = n_pre + ntok + n_post
     ids = torch.randint(0, 150000, (1, n_pre + n_post), device=dev)
     embed = llm.get_input_embeddings()
+    prefill = pkg.LlmPrefill.from_hf(llm, max_seq=seq, device=dev)
+    xin = prefill.input(seq).view(1, seq, hidden)
 
-    def one():
+    def one_native():
         t0 = time.perf_counter()
         pkg.preprocess_into(eng, host_u8, img[0])     # uint8 H2D + resize/crop/scale on the GPU (row f1)
-        x = torch.empty(1, n_pre + ntok + n_post, hidden, dtype=torch.bfloat16, device=dev)
-        eng.forward_into(img, x, n_pre)             # projector epilogue stores at the <image> position (row f2)
+        eng.forward_into(img, xin, n_pre)             # projector epilogue stores at the <image> position of the LLM input (row f2)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        txt = embed(ids)
+        xin[:, :n_pre] = txt[:, :n_pre]
+        xin[:, n_pre + ntok:] = txt[:, n_pre:]
+        tok, _ = prefill.prefill(seq)                 # row f3; returns after the token reached the host
+        t2 = time.perf_counter()
+        return (t2 - t0) * 1e3, (t1 - t0) * 1e3, (t2 - t1) * 1e3, tok
+
+    def one_hf():
+        t0 = time.perf_counter()
+        pkg.preprocess_into(eng, host_u8, img[0])
+        x = torch.empty(1, seq, hidden, dtype=torch.bfloat16, device=dev)
+        eng.forward_into(img, x, n_pre)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         txt = embed(ids)
         x[:, :n_pre] = txt[:, :n_pre]
         x[:, n_pre + ntok:] = txt[:, n_pre:]
-        llm(inputs_embeds=x, use_cache=True).logits[:, -1].argmax(-1).item()      # first token on the host
+        tok = llm(inputs_embeds=x, use_cache=True).logits[:, -1].argmax(-1).item()      # first token on the host
         t2 = time.perf_counter()
-        return (t2 - t0) * 1e3, (t1 - t0) * 1e3, (t2 - t1) * 1e3
+        return (t2 - t0) * 1e3, (t1 - t0) * 1e3, (t2 - t1) * 1e3, tok
 
     with torch.inference_mode():
         for _ in range(warmup):
-            one()
-        rs = [one() for _ in range(runs)]
-    del llm, eng
+            one_native()
+        rs = [one_native() for _ in range(runs)]
+        hf_runs = max(10, runs // 3)
+        for _ in range(3):
+            one_hf()
+        hs = [one_hf() for _ in range(hf_runs)]
+        # same weights, same input: logits of the two prefills (random-init logits are nearly flat, so compare the vectors, not only argmax)
+        _, lg = prefill.prefill(seq, want_logits=True)
+        lh = llm(inputs_embeds=xin.clone(), use_cache=False).logits[0, -1].float()
+        logit_err = ((lg.float() - lh).norm() / lh.norm()).item()
+    launches = prefill.launches(seq)
+    del llm, eng, prefill
     torch.cuda.empty_cache()
     tt = sorted(r[0] for r in rs)
     return {"ttft_ms_p50": statistics.median(tt), "encode_ms_p50": statistics.median(r[1] for r in rs),
             "prefill_first_token_ms_p50": statistics.median(r[2] for r in rs), "ttft_ms_min": tt[0], "ttft_ms_p90": tt[int(0.9 * (len(tt) - 1))],
-            "runs": runs, "warmup": warmup, "sequence": n_pre + ntok + n_post, "resolution": res, "visual_tokens": ntok}
+            "runs": runs, "warmup": warmup, "sequence": seq, "resolution": res, "visual_tokens": ntok,
+            "prefill": "library (row f3): tcgen05 GEMMs + RMSNorm / RoPE / causal GQA attention / SwiGLU / argmax kernels, one CUDA graph",
+            "prefill_launches": launches,
+            "hf_prefill": {"ttft_ms_p50": statistics.median(r[0] for r in hs), "prefill_first_token_ms_p50": statistics.median(r[2] for r in hs),
+                           "runs": hf_runs, "impl": "stock transformers Qwen2ForCausalLM.forward (eager), same weights and input"},
+            "first_token_equal_to_hf": bool(rs[-1][3] == hs[-1][3]), "last_logits_rel_l2_vs_hf_bf16": logit_err}
 
 
 QWEN2_05B = dict(hidden_size=896, num_hidden_layers=24, num_attention_heads=14, num_key_value_heads=2, intermediate_size=4864,
@@ -492,15 +525,15 @@ def run_gpu_arm(args):
         try:
             t3 = ttft_run(dev, RES, HIDDEN, QWEN2_05B, args.ttft_runs, 5, pkg, fx)
             t3["ttft_ms_p50_max_over_ranks"] = allmax([t3["ttft_ms_p50"]])[0]
-            t3["llm"] = "random-init Qwen2ForCausalLM (Qwen2-0.5B shape), bf16, stock transformers (prefill is row f3, not rebuilt)"
+            t3["llm"] = "random-init Qwen2ForCausalLM (Qwen2-0.5B shape), bf16 weights"
             ttft = {"config3": t3}
             if args.ttft7b or world == 8:
                 t5 = ttft_run(dev, 1536, 3584, QWEN2_7B, max(10, args.ttft_runs // 2), 3, pkg, fx)
                 t5["ttft_ms_p50_max_over_ranks"] = allmax([t5["ttft_ms_p50"]])[0]
-                t5["llm"] = "random-init Qwen2ForCausalLM (Qwen2-7B shape), bf16, stock transformers"
+                t5["llm"] = "random-init Qwen2ForCausalLM (Qwen2-7B shape), bf16 weights"
                 ttft["config5"] = t5
             ttft["note"] = ("one replica per GPU: a single image is not sharded, so TTFT is flat in N by design; "
-                            "TTFT = uint8 host image -> H2D -> GPU preprocessing -> encode_images (splice store) -> HF prefill -> first token")
+                            "TTFT = uint8 host image -> H2D -> GPU preprocessing -> encode_images (splice store) -> LLM prefill -> first token")
         except Exception as e:  # noqa: BLE001
             ttft = {"unavailable": repr(e)[:300]}
 

@@ -58,6 +58,21 @@ typedef struct {
     int64_t numel;
 } fvhd_tensor;
 
+/* Decoder configuration of the LLM whose prefill follows encode_images (row f3): the fields of transformers' Qwen2Config that
+ * Qwen2ForCausalLM.forward reads (llava/model/language_model/llava_qwen.py:33-55: LlavaQwen2ForCausalLM subclasses it unchanged). */
+typedef struct {
+    int hidden;                 /* hidden_size */
+    int layers;                 /* num_hidden_layers */
+    int heads;                  /* num_attention_heads */
+    int kv_heads;               /* num_key_value_heads (grouped-query attention) */
+    int head_dim;               /* hidden_size / num_attention_heads: 64 or 128 */
+    int intermediate;           /* intermediate_size */
+    int vocab;                  /* vocab_size */
+    int max_seq;                /* longest prompt (text + visual tokens) a prefill may have */
+    float rope_theta;
+    float rms_eps;
+} fvhd_llm_config;
+
 typedef struct fvhd_handle_s* fvhd_handle;
 
 /* replaces: MobileCLIPVisionTower.__init__ / load_model (mobileclip_encoder.py:14-58) and
@@ -197,6 +212,27 @@ int fvhd_mixer(fvhd_handle h, void* stream, const void* x, const void* w3, const
  * only, may be NULL) receives 64 globaltimer stamps per CTA. */
 int fvhd_convffn(fvhd_handle h, void* stream, const void* z, const void* w1, const void* b1, const void* w2, const void* b2,
                  const void* resid, void* out, int M, int C, void* trace_64_u64_per_cta);
+
+/* ---- row f3: LLM prefill (time to first token) ------------------------------------------------------------------------------
+ * replaces: the first call of LlavaQwen2ForCausalLM.forward inside generate() (llava_qwen.py:57-103 -> transformers
+ * Qwen2ForCausalLM.forward -> Qwen2Model.forward: 24 x [RMSNorm, q/k/v proj + bias, RoPE, causal GQA attention, o proj, RMSNorm,
+ * SwiGLU MLP], final RMSNorm, lm_head on the last position; predict.py:58-65) for ONE sequence of L spliced embeddings.
+ * The four GEMMs of a layer run on the tower's tcgen05 GEMM kernel; RMSNorm / RoPE / attention / SwiGLU / argmax are llm.cuh.
+ *
+ * fvhd_llm_load: `weights` are caller-owned DEVICE pointers, 7 per layer then 2:
+ *     ln1 f32[H] | wqkv bf16[(heads+2kv)*D, H] (q rows, k rows, v rows) | bqkv f32[(heads+2kv)*D] | wo bf16[H, heads*D] | ln2 f32[H] |
+ *     wgu bf16[2I, H] (gate rows then up rows) | wd bf16[H, I]      ...      final_norm f32[H] | lm_head bf16[V, H]
+ * Activations, the RoPE table and a KV cache [layers, max_seq, kv*D] x 2 are owned by the handle.
+ * fvhd_llm_input: device buffer [max_seq, H] bf16 the caller fills with the spliced sequence (text embeddings + visual tokens; the
+ *     projector epilogue can store straight into it: fvhd_forward_strided / _scatter).
+ * fvhd_llm_prefill: runs the L-token prefill as one CUDA graph on `stream`; optionally copies the last position's logits
+ *     (bf16 [V], device) and the argmax token (int32, device or pinned host) out.  Does not synchronise.
+ * fvhd_llm_kv_cache: the K (post-RoPE) and V rows of every layer written by the last prefill, for the decode loop. */
+int fvhd_llm_load(fvhd_handle h, const fvhd_llm_config* cfg, const void* const* weights, int n_weights);
+void* fvhd_llm_input(fvhd_handle h);
+int fvhd_llm_prefill(fvhd_handle h, void* stream, int L, void* logits_out, int* token_out);
+int fvhd_llm_kv_cache(fvhd_handle h, void** k_out, void** v_out);
+int fvhd_llm_launches(fvhd_handle h, int L);
 
 #ifdef __cplusplus
 }

@@ -26,6 +26,7 @@
 #include "mixer_tc2.cuh"
 #include "mixer_tz.cuh"
 #include "stem2.cuh"
+#include "llm.cuh"
 #include "convffn.cuh"
 #include "attention_umma.cuh"
 
@@ -76,7 +77,21 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 }  // namespace
 
+// LLM prefill engine attached to a handle (row f3): caller-owned weights, library-owned activations / KV cache, one plan per length.
+struct LlmState {
+    fvhd_llm_config c{};
+    int nqkv = 0;                       // (heads + 2 kv_heads) * head_dim
+    std::vector<const void*> w;         // 7 per layer + final norm + lm_head
+    bf16 *x0 = nullptr, *x1 = nullptr, *x2 = nullptr, *xn = nullptr;      // x0: the caller's input (never written by a prefill)
+    bf16 *qkv = nullptr, *att = nullptr, *gu = nullptr, *hm = nullptr, *logits = nullptr;
+    bf16 *kc = nullptr, *vc = nullptr;  // [layers][max_seq][kv_heads * head_dim]
+    float2* rope = nullptr;             // [max_seq][head_dim / 2]
+    int* token = nullptr;
+    std::map<int, Plan> plans;          // key: sequence length
+};
+
 struct fvhd_handle_s {
+    LlmState* llm = nullptr;
     fvhd_config cfg;
     std::string err;
     int R = 0, ntok = 0;
@@ -1102,6 +1117,80 @@ int run_forward(fvhd_handle h, Plan& pl, cudaStream_t st, const RunCtx& ctx, int
     return FVHD_OK;
 }
 
+// ------------------------------------------------------------------ LLM prefill (row f3)
+void llm_free(LlmState* L) {
+    for (auto& kv : L->plans)
+        for (auto& g : kv.second.graphs) cudaGraphExecDestroy(g.second);
+    L->plans.clear();
+    void* bufs[] = {L->x0, L->x1, L->x2, L->xn, L->qkv, L->att, L->gu, L->hm, L->logits, L->kc, L->vc, L->rope, L->token};
+    for (void* b : bufs) if (b) cudaFree(b);
+}
+
+// Launch sequence of one L-token prefill: per layer RMSNorm, qkv GEMM (+bias), RoPE (+KV cache), causal GQA attention, o GEMM (+residual),
+// RMSNorm, gate/up GEMM, SwiGLU, down GEMM (+residual); then final RMSNorm on the last row, lm_head GEMM (M = 1), argmax.
+int build_llm_plan(fvhd_handle h, LlmState* S, int L, Plan& pl) {
+    const fvhd_llm_config& c = S->c;
+    const int H = c.hidden, D = c.head_dim, I = c.intermediate, NQ = S->nqkv, HD = c.heads * D;
+    pl = Plan();
+    pl.batch = L;
+    int rc;
+    bf16 *xc = S->x0, *xx = S->x1;           // layer input (x0 = the caller's sequence, then x2) / post-attention stream
+    const int ln_grid = (L + 7) / 8;
+    const float sl2 = 1.4426950408889634f / sqrtf((float)D);
+    const float2* rope = S->rope;
+    auto add_gemm_l = [&](const bf16* A, int lda, const void* W, const void* bias, const bf16* resid, bf16* Dp, int M, int N, int K) -> int {
+        Step g;
+        int r = make_gemm_step(h, &g, nullptr, 1, A, lda, (const bf16*)W, (const float*)bias, resid, N, Dp, N, M, N, K, 0);
+        if (r != FVHD_OK) return r;
+        pl.add(g, kGemm, 0, gemm_flops(M, N, K), 2.0 * ((double)M * K + (double)N * K + (double)M * N));
+        return FVHD_OK;
+    };
+    for (int l = 0; l < c.layers; ++l) {
+        const void* const* w = S->w.data() + (size_t)l * 7;
+        const float *ln1 = (const float*)w[0], *ln2 = (const float*)w[4];
+        bf16 *xn = S->xn, *qkv = S->qkv, *att = S->att, *gu = S->gu, *hm = S->hm;
+        bf16* kc = S->kc + (size_t)l * c.max_seq * c.kv_heads * D;
+        bf16* vc = S->vc + (size_t)l * c.max_seq * c.kv_heads * D;
+        const bf16* xin = xc;
+        const float eps = c.rms_eps;
+        pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t { return launch_k(rmsnorm_kernel, dim3(ln_grid), dim3(256), 0, s, xin, xn, ln1, L, H, eps); },
+               "rmsnorm_kernel", 0, 0.0, 4.0 * L * H);
+        if ((rc = add_gemm_l(xn, H, w[1], w[2], nullptr, qkv, L, NQ, H)) != FVHD_OK) return rc;
+        const int heads = c.heads, kvh = c.kv_heads;
+        const int rgrid = (int)std::min<long>(((long)L * (heads + kvh) * (D / 2) + 255) / 256, 1184);
+        pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t { return launch_k(rope_kv_kernel, dim3(rgrid), dim3(256), 0, s, qkv, rope, kc, vc, L, heads, kvh, D); },
+               "rope_kv_kernel", 0, 0.0, 4.0 * L * NQ);
+        const dim3 agrid((L + 31) / 32, heads);
+        pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+                   if (D == 64) return launch_k(causal_attn_kernel<64>, agrid, dim3(256), LlmAttnSmem<64>::BYTES, s, (const bf16*)qkv, att, L, heads, kvh, sl2);
+                   return launch_k(causal_attn_kernel<128>, agrid, dim3(256), LlmAttnSmem<128>::BYTES, s, (const bf16*)qkv, att, L, heads, kvh, sl2);
+               }, "causal_attn_kernel", 0, 2.0 * (double)L * L * HD, 2.0 * L * (NQ + HD));
+        if ((rc = add_gemm_l(att, HD, w[3], nullptr, xc, xx, L, H, HD)) != FVHD_OK) return rc;
+        const bf16* x2 = xx;
+        pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t { return launch_k(rmsnorm_kernel, dim3(ln_grid), dim3(256), 0, s, x2, xn, ln2, L, H, eps); },
+               "rmsnorm_kernel", 0, 0.0, 4.0 * L * H);
+        if ((rc = add_gemm_l(xn, H, w[5], nullptr, nullptr, gu, L, 2 * I, H)) != FVHD_OK) return rc;
+        const int sgrid = (int)std::min<long>(((long)L * (I / 8) + 255) / 256, 1184);
+        pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t { return launch_k(silu_mul_kernel, dim3(sgrid), dim3(256), 0, s, (const bf16*)gu, hm, L, I); },
+               "silu_mul_kernel", 0, 0.0, 6.0 * L * I);
+        if ((rc = add_gemm_l(hm, I, w[6], nullptr, xx, S->x2, L, H, I)) != FVHD_OK) return rc;
+        xc = S->x2;                              // the input buffer x0 is only ever read: a prefill can be replayed
+    }
+    const float* fn = (const float*)S->w[(size_t)c.layers * 7];
+    const void* lm = S->w[(size_t)c.layers * 7 + 1];
+    const bf16* last = xc + (size_t)(L - 1) * H;
+    bf16 *xn = S->xn, *logits = S->logits;
+    int* tok = S->token;
+    const float eps = c.rms_eps;
+    const int V = c.vocab;
+    pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t { return launch_k(rmsnorm_kernel, dim3(1), dim3(256), 0, s, last, xn, fn, 1, H, eps); },
+           "rmsnorm_kernel", 0, 0.0, 4.0 * H);
+    if ((rc = add_gemm_l(xn, H, lm, nullptr, nullptr, logits, 1, V, H)) != FVHD_OK) return rc;
+    pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t { return launch_k(argmax_kernel, dim3(1), dim3(1024), 0, s, (const bf16*)logits, V, tok); },
+           "argmax_kernel", 0, 0.0, 2.0 * V);
+    return FVHD_OK;
+}
+
 void destroy_plans(fvhd_handle h) {
     for (auto& kv : h->plans)
         for (auto& g : kv.second.graphs) cudaGraphExecDestroy(g.second);
@@ -1144,6 +1233,7 @@ int fvhd_destroy(fvhd_handle h) {
         if (h->rs_tmp) cudaFree(h->rs_tmp);
         if (h->rs_src) cudaFree(h->rs_src);
         if (h->rs_lut) cudaFree(h->rs_lut);
+        if (h->llm) { llm_free(h->llm); delete h->llm; }
     }
     delete h;
     return FVHD_OK;
@@ -1709,5 +1799,87 @@ int fvhd_convffn(fvhd_handle h, void* stream, const void* z, const void* w1, con
     return FVHD_OK;
 }
 
+
+// ------------------------------------------------------------------ row f3: LLM prefill
+int fvhd_llm_load(fvhd_handle h, const fvhd_llm_config* cfg, const void* const* weights, int n_weights) {
+    if (!h || !cfg || !weights) return FVHD_ERR_INVALID;
+    int rc = ensure_cuda(h);
+    if (rc != FVHD_OK) return rc;
+    const fvhd_llm_config& c = *cfg;
+    if (c.hidden < 8 || c.hidden % 8 || c.layers < 1 || c.heads < 1 || c.kv_heads < 1 || c.heads % c.kv_heads || (c.head_dim != 64 && c.head_dim != 128) ||
+        c.intermediate % 8 || c.vocab % 8 || c.max_seq < 1)
+        return fail(h, FVHD_ERR_INVALID, "fvhd_llm_load: unsupported config (hidden %d, heads %d / %d, head_dim %d, intermediate %d, vocab %d)", c.hidden, c.heads,
+                    c.kv_heads, c.head_dim, c.intermediate, c.vocab);
+    if (n_weights != c.layers * 7 + 2) return fail(h, FVHD_ERR_INVALID, "fvhd_llm_load: expected %d weight pointers, got %d", c.layers * 7 + 2, n_weights);
+    for (int i = 0; i < n_weights; ++i)
+        if (!weights[i] || ((uintptr_t)weights[i] & 15)) return fail(h, FVHD_ERR_INVALID, "fvhd_llm_load: weight %d is null or not 16-byte aligned", i);
+    if (h->llm) { llm_free(h->llm); delete h->llm; h->llm = nullptr; }
+    LlmState* S = new LlmState();
+    S->c = c;
+    S->nqkv = (c.heads + 2 * c.kv_heads) * c.head_dim;
+    S->w.assign(weights, weights + n_weights);
+    const size_t T = (size_t)c.max_seq;
+    auto alloc = [&](void** p, size_t bytes) { return cudaMalloc(p, bytes) == cudaSuccess; };
+    bool ok = alloc((void**)&S->x0, T * c.hidden * 2) && alloc((void**)&S->x1, T * c.hidden * 2) && alloc((void**)&S->x2, T * c.hidden * 2) &&
+              alloc((void**)&S->xn, T * c.hidden * 2) &&
+              alloc((void**)&S->qkv, T * S->nqkv * 2) && alloc((void**)&S->att, T * c.heads * c.head_dim * 2) && alloc((void**)&S->gu, T * 2 * c.intermediate * 2) &&
+              alloc((void**)&S->hm, T * c.intermediate * 2) && alloc((void**)&S->logits, (size_t)c.vocab * 2) &&
+              alloc((void**)&S->kc, (size_t)c.layers * T * c.kv_heads * c.head_dim * 2) && alloc((void**)&S->vc, (size_t)c.layers * T * c.kv_heads * c.head_dim * 2) &&
+              alloc((void**)&S->rope, T * (c.head_dim / 2) * sizeof(float2)) && alloc((void**)&S->token, sizeof(int));
+    if (!ok) { (void)cudaGetLastError(); llm_free(S); delete S; return fail(h, FVHD_ERR_CUDA, "fvhd_llm_load: out of device memory"); }
+    const int n = c.max_seq * (c.head_dim / 2);
+    rope_table_kernel<<<(n + 255) / 256, 256>>>(S->rope, c.max_seq, c.head_dim / 2, c.rope_theta);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    CUDA_TRY(h, set_smem(causal_attn_kernel<64>, LlmAttnSmem<64>::BYTES));
+    CUDA_TRY(h, set_smem(causal_attn_kernel<128>, LlmAttnSmem<128>::BYTES));
+    h->llm = S;
+    return FVHD_OK;
+}
+
+void* fvhd_llm_input(fvhd_handle h) { return (h && h->llm) ? h->llm->x0 : nullptr; }
+
+int fvhd_llm_kv_cache(fvhd_handle h, void** k_out, void** v_out) {
+    if (!h || !h->llm) return FVHD_ERR_INVALID;
+    if (k_out) *k_out = h->llm->kc;
+    if (v_out) *v_out = h->llm->vc;
+    return FVHD_OK;
+}
+
+static int llm_plan(fvhd_handle h, int L, Plan** out) {
+    LlmState* S = h->llm;
+    if (!S) return fail(h, FVHD_ERR_INVALID, "no LLM loaded (fvhd_llm_load)");
+    if (L < 1 || L > S->c.max_seq) return fail(h, FVHD_ERR_INVALID, "prefill length %d outside [1, %d]", L, S->c.max_seq);
+    auto it = S->plans.find(L);
+    if (it == S->plans.end()) {
+        Plan pl;
+        int rc = build_llm_plan(h, S, L, pl);
+        if (rc != FVHD_OK) return rc;
+        it = S->plans.emplace(L, std::move(pl)).first;
+    }
+    *out = &it->second;
+    return FVHD_OK;
+}
+
+int fvhd_llm_launches(fvhd_handle h, int L) {
+    if (!h) return FVHD_ERR_INVALID;
+    Plan* pl = nullptr;
+    int rc = llm_plan(h, L, &pl);
+    return rc != FVHD_OK ? rc : (int)pl->steps.size();
+}
+
+int fvhd_llm_prefill(fvhd_handle h, void* stream, int L, void* logits_out, int* token_out) {
+    if (!h) return FVHD_ERR_INVALID;
+    Plan* pl = nullptr;
+    int rc = llm_plan(h, L, &pl);
+    if (rc != FVHD_OK) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    RunCtx ctx{};
+    if ((rc = run_forward(h, *pl, st, ctx, (int)pl->steps.size(), nullptr, 0)) != FVHD_OK) return rc;
+    LlmState* S = h->llm;
+    if (logits_out) CUDA_TRY(h, cudaMemcpyAsync(logits_out, S->logits, (size_t)S->c.vocab * 2, cudaMemcpyDeviceToDevice, st));
+    if (token_out) CUDA_TRY(h, cudaMemcpyAsync(token_out, S->token, sizeof(int), cudaMemcpyDefault, st));
+    return FVHD_OK;
+}
 
 }  // extern "C"

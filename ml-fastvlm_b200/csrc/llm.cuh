@@ -1,0 +1,272 @@
+// LLM prefill (row f3: the caller of encode_images, llava_qwen.py:57-143 -> transformers Qwen2ForCausalLM.forward on the spliced
+// [1, L, H] embedding sequence; TTFT = this pass + the first token, FastVLMModel.swift:114-138).  The four GEMMs of a decoder layer
+// run on the tcgen05 GEMM kernel of the tower (gemm_tcgen05.cuh: bias / residual epilogues, split-K at small M); this header holds
+// the glue kernels a Qwen2 layer needs around them:
+//     rmsnorm_kernel        Qwen2RMSNorm: y = w * x * rsqrt(mean(x^2) + eps)                        (modeling_qwen2.py Qwen2RMSNorm.forward)
+//     rope_table_kernel     cos / sin of pos * theta^(-2d/D), fp32, built once per handle          (Qwen2RotaryEmbedding)
+//     rope_kv_kernel        rotate_half RoPE in place on the q and k heads of the fused qkv rows; K / V rows copied to the KV cache
+//     causal_attn_kernel<D> causal GQA attention, flash-style over 64-key tiles, fp32 softmax / accumulation on the FMA pipes
+//                           (L = 287 tokens x 14 heads: 0.3 GFLOP per layer -- latency, not throughput, matters here)
+//     silu_mul_kernel       SwiGLU gate: h = silu(gate) * up                                         (Qwen2MLP.forward)
+//     argmax_kernel         first token = argmax of the last position's logits
+#pragma once
+#include "ptx.cuh"
+
+namespace fvhd {
+
+// one warp per row; H % 8 == 0
+__global__ void __launch_bounds__(256)
+rmsnorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ w, int rows, int H, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * H);
+    const int nv = H / 8;
+    float ss = 0.f;
+    for (int v = lane; v < nv; v += 32) {
+        const uint4 u = __ldg(xr + v);
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float r = rsqrtf(ss / (float)H + eps);
+    uint4* yr = reinterpret_cast<uint4*>(y + (size_t)row * H);
+    for (int v = lane; v < nv; v += 32) {
+        const uint4 u = __ldg(xr + v);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + 2 * v), w1 = __ldg(reinterpret_cast<const float4*>(w) + 2 * v + 1);
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        uint4 o;
+        o.x = pack_bf16x2(a.x * r * w0.x, a.y * r * w0.y);
+        o.y = pack_bf16x2(b.x * r * w0.z, b.y * r * w0.w);
+        o.z = pack_bf16x2(c.x * r * w1.x, c.y * r * w1.y);
+        o.w = pack_bf16x2(d.x * r * w1.z, d.y * r * w1.w);
+        yr[v] = o;
+    }
+}
+
+// table[pos][d] = (cos, sin)(pos * theta^(-2 d / D)), d < D / 2
+__global__ void rope_table_kernel(float2* __restrict__ table, int max_pos, int half, float theta) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= max_pos * half) return;
+    const int pos = i / half, d = i - pos * half;
+    const float inv = exp2f(-(float)d / (float)half * log2f(theta));          // theta^(-2d/D), fp32 as in the reference
+    float s, c;
+    sincosf((float)pos * inv, &s, &c);
+    table[i] = make_float2(c, s);
+}
+
+// qkv rows [L, (heads + 2 kv) * D]: rotate_half RoPE on the q and k heads (positions 0..L-1), in place; K and V rows -> cache (optional)
+__global__ void __launch_bounds__(256)
+rope_kv_kernel(bf16* __restrict__ qkv, const float2* __restrict__ table, bf16* __restrict__ k_cache, bf16* __restrict__ v_cache,
+               int L, int heads, int kv_heads, int D) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int half = D / 2;
+    const int ld = (heads + 2 * kv_heads) * D;
+    const int per_tok = (heads + kv_heads) * half;
+    const long total = (long)L * per_tok;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int tok = (int)(i / per_tok), r = (int)(i - (long)tok * per_tok);
+        const int hd = r / half, d = r - hd * half;                 // hd < heads: q head; else k head
+        bf16* p = qkv + (size_t)tok * ld + (size_t)hd * D + d;
+        const float2 cs = table[(size_t)tok * half + d];
+        const float x1 = __bfloat162float(p[0]), x2 = __bfloat162float(p[half]);
+        const bf16 o1 = __float2bfloat16_rn(x1 * cs.x - x2 * cs.y), o2 = __float2bfloat16_rn(x2 * cs.x + x1 * cs.y);
+        p[0] = o1; p[half] = o2;
+        if (k_cache && hd >= heads) {
+            bf16* kc = k_cache + ((size_t)tok * kv_heads + (hd - heads)) * D + d;
+            kc[0] = o1; kc[half] = o2;
+        }
+    }
+    if (v_cache) {
+        const long nv = (long)L * kv_heads * D;
+        for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long)gridDim.x * blockDim.x) {
+            const int tok = (int)(i / (kv_heads * D)), r = (int)(i - (long)tok * kv_heads * D);
+            v_cache[i] = qkv[(size_t)tok * ld + (size_t)(heads + kv_heads) * D + r];
+        }
+    }
+}
+
+template <int D> struct LlmAttnSmem { static constexpr size_t BYTES = (size_t)2 * 64 * (D + 8) * 2 + (size_t)32 * D * 4; };
+
+// Causal grouped-query attention over RoPE'd qkv rows.  grid (ceil(L / 32), heads); 8 warps x 4 queries; 64-key tiles in smem.
+// out [L, heads * D] bf16.  scale_log2 = D^-0.5 * log2(e).
+template <int D>
+__global__ void __launch_bounds__(256)
+causal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int heads, int kv_heads, float scale_log2) {
+    constexpr int TK = 64, QB = 32, NQ = 4, KP = D + 8;          // key pitch (halves): +16 B keeps the 16-B row reads conflict-free
+    constexpr int DW = D / 64;                                   // bf16x2 words of V / o per lane
+    extern __shared__ __align__(16) uint8_t attn_smem[];         // LlmAttnSmem<D>::BYTES
+    bf16* Ks = reinterpret_cast<bf16*>(attn_smem);
+    bf16* Vs = Ks + TK * KP;
+    float* Qs = reinterpret_cast<float*>(Vs + TK * KP);
+    pdl_launch_dependents();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int hq = blockIdx.y, hk = hq / (heads / kv_heads);
+    const int q0 = blockIdx.x * QB;
+    const int ld = (heads + 2 * kv_heads) * D;
+    pdl_wait();
+    // this CTA's queries, pre-scaled, fp32
+    for (int i = threadIdx.x; i < QB * D / 2; i += 256) {
+        const int qi = i / (D / 2), dp = i - qi * (D / 2);
+        float2 v = make_float2(0.f, 0.f);
+        if (q0 + qi < L) v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qkv + (size_t)(q0 + qi) * ld + (size_t)hq * D + 2 * dp));
+        Qs[qi * D + 2 * dp] = v.x * scale_log2;
+        Qs[qi * D + 2 * dp + 1] = v.y * scale_log2;
+    }
+    float m[NQ], l[NQ], o[NQ][2 * DW];
+#pragma unroll
+    for (int t = 0; t < NQ; ++t) {
+        m[t] = -1e30f; l[t] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 2 * DW; ++e) o[t][e] = 0.f;
+    }
+    const int q_last = min(q0 + QB, L) - 1;
+    const int qw = q0 + warp * NQ;                               // this warp's first query
+    for (int k0 = 0; k0 <= q_last; k0 += TK) {
+        __syncthreads();                                         // previous tile consumed (and Qs written)
+        for (int i = threadIdx.x; i < TK * D / 8; i += 256) {
+            const int kj = i / (D / 8), c = i - kj * (D / 8);
+            uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+            if (k0 + kj < L) {
+                const bf16* row = qkv + (size_t)(k0 + kj) * ld;
+                kv = *reinterpret_cast<const uint4*>(row + (size_t)(heads + hk) * D + c * 8);
+                vv = *reinterpret_cast<const uint4*>(row + (size_t)(heads + kv_heads + hk) * D + c * 8);
+            }
+            *reinterpret_cast<uint4*>(Ks + kj * KP + c * 8) = kv;
+            *reinterpret_cast<uint4*>(Vs + kj * KP + c * 8) = vv;
+        }
+        __syncthreads();
+        if (k0 > qw + NQ - 1) continue;                          // every key of the tile is in this warp's future (barriers stay uniform)
+        // ---- scores: lane owns keys `lane` and `lane + 32` of the tile
+        float s[NQ][2];
+#pragma unroll
+        for (int t = 0; t < NQ; ++t) s[t][0] = s[t][1] = 0.f;
+#pragma unroll 2
+        for (int c = 0; c < D / 8; ++c) {
+            const uint4 ka = *reinterpret_cast<const uint4*>(Ks + lane * KP + c * 8);
+            const uint4 kb = *reinterpret_cast<const uint4*>(Ks + (lane + 32) * KP + c * 8);
+            float fa[8], fb[8];
+            { float2 v;
+              v = unpack_bf16x2(ka.x); fa[0] = v.x; fa[1] = v.y; v = unpack_bf16x2(ka.y); fa[2] = v.x; fa[3] = v.y;
+              v = unpack_bf16x2(ka.z); fa[4] = v.x; fa[5] = v.y; v = unpack_bf16x2(ka.w); fa[6] = v.x; fa[7] = v.y;
+              v = unpack_bf16x2(kb.x); fb[0] = v.x; fb[1] = v.y; v = unpack_bf16x2(kb.y); fb[2] = v.x; fb[3] = v.y;
+              v = unpack_bf16x2(kb.z); fb[4] = v.x; fb[5] = v.y; v = unpack_bf16x2(kb.w); fb[6] = v.x; fb[7] = v.y; }
+#pragma unroll
+            for (int t = 0; t < NQ; ++t) {
+                const float4 qa = *reinterpret_cast<const float4*>(Qs + (warp * NQ + t) * D + c * 8);
+                const float4 qb = *reinterpret_cast<const float4*>(Qs + (warp * NQ + t) * D + c * 8 + 4);
+                s[t][0] += qa.x * fa[0] + qa.y * fa[1] + qa.z * fa[2] + qa.w * fa[3] + qb.x * fa[4] + qb.y * fa[5] + qb.z * fa[6] + qb.w * fa[7];
+                s[t][1] += qa.x * fb[0] + qa.y * fb[1] + qa.z * fb[2] + qa.w * fb[3] + qb.x * fb[4] + qb.y * fb[5] + qb.z * fb[6] + qb.w * fb[7];
+            }
+        }
+        // ---- online softmax per query, then o += P V
+#pragma unroll
+        for (int t = 0; t < NQ; ++t) {
+            const int qi = qw + t;
+            const bool a_ok = k0 + lane <= qi && k0 + lane < L, b_ok = k0 + lane + 32 <= qi && k0 + lane + 32 < L;
+            const float sa = a_ok ? s[t][0] : -1e30f, sb = b_ok ? s[t][1] : -1e30f;
+            float mx = fmaxf(sa, sb);
+#pragma unroll
+            for (int of = 16; of > 0; of >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, of));
+            const float mn = fmaxf(m[t], mx);
+            const float pa = a_ok ? exp2f(sa - mn) : 0.f, pb = b_ok ? exp2f(sb - mn) : 0.f;
+            float ps = pa + pb;
+#pragma unroll
+            for (int of = 16; of > 0; of >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, of);
+            const float corr = exp2f(m[t] - mn);
+            m[t] = mn;
+            l[t] = l[t] * corr + ps;
+#pragma unroll
+            for (int e = 0; e < 2 * DW; ++e) o[t][e] *= corr;
+            s[t][0] = pa; s[t][1] = pb;
+        }
+#pragma unroll 4
+        for (int kj = 0; kj < 32; ++kj) {
+            float2 va[DW], vb[DW];
+#pragma unroll
+            for (int e = 0; e < DW; ++e) {
+                va[e] = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(Vs + kj * KP + 2 * (lane + 32 * e)));
+                vb[e] = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(Vs + (kj + 32) * KP + 2 * (lane + 32 * e)));
+            }
+#pragma unroll
+            for (int t = 0; t < NQ; ++t) {
+                const float pa = __shfl_sync(0xffffffffu, s[t][0], kj), pb = __shfl_sync(0xffffffffu, s[t][1], kj);
+#pragma unroll
+                for (int e = 0; e < DW; ++e) {
+                    o[t][2 * e] += pa * va[e].x + pb * vb[e].x;
+                    o[t][2 * e + 1] += pa * va[e].y + pb * vb[e].y;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < NQ; ++t) {
+        const int qi = qw + t;
+        if (qi < L) {
+            const float inv = 1.f / l[t];
+#pragma unroll
+            for (int e = 0; e < DW; ++e)
+                *reinterpret_cast<uint32_t*>(out + (size_t)qi * heads * D + (size_t)hq * D + 2 * (lane + 32 * e)) = pack_bf16x2(o[t][2 * e] * inv, o[t][2 * e + 1] * inv);
+        }
+    }
+}
+
+// gu [rows, 2 I] (gate columns then up columns) -> h [rows, I] = silu(gate) * up
+__global__ void __launch_bounds__(256)
+silu_mul_kernel(const bf16* __restrict__ gu, bf16* __restrict__ hm, int rows, int I) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int nv = I / 8;
+    const long total = (long)rows * nv;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / nv), v = (int)(i - (long)r * nv);
+        const uint4 g = *reinterpret_cast<const uint4*>(gu + (size_t)r * 2 * I + v * 8);
+        const uint4 u = *reinterpret_cast<const uint4*>(gu + (size_t)r * 2 * I + I + v * 8);
+        const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, uw[4] = {u.x, u.y, u.z, u.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 a = unpack_bf16x2(gw[k]), b = unpack_bf16x2(uw[k]);
+            ow[k] = pack_bf16x2(a.x / (1.f + __expf(-a.x)) * b.x, a.y / (1.f + __expf(-a.y)) * b.y);
+        }
+        *reinterpret_cast<uint4*>(hm + (size_t)r * I + v * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+}
+
+// one CTA: index of the largest of n bf16 logits (lowest index on ties, as torch.argmax)
+__global__ void __launch_bounds__(1024)
+argmax_kernel(const bf16* __restrict__ logits, int n, int* __restrict__ out) {
+    __shared__ float bv[32];
+    __shared__ int bi[32];
+    pdl_launch_dependents();
+    pdl_wait();
+    float best = -INFINITY;
+    int idx = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const float v = __bfloat162float(logits[i]);
+        if (v > best || (v == best && i < idx)) { best = v; idx = i; }
+    }
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, of);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, of);
+        if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = bv[threadIdx.x]; idx = bi[threadIdx.x];
+#pragma unroll
+        for (int of = 16; of > 0; of >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, of);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, of);
+            if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+        }
+        if (threadIdx.x == 0) *out = idx;
+    }
+}
+
+}  // namespace fvhd

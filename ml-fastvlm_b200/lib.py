@@ -17,6 +17,11 @@ class FvhdConfig(C.Structure):
     _fields_ = [("image_size", C.c_int), ("projector_hidden", C.c_int), ("projector_depth", C.c_int), ("max_batch", C.c_int)]
 
 
+class FvhdLlmConfig(C.Structure):
+    _fields_ = [("hidden", C.c_int), ("layers", C.c_int), ("heads", C.c_int), ("kv_heads", C.c_int), ("head_dim", C.c_int),
+                ("intermediate", C.c_int), ("vocab", C.c_int), ("max_seq", C.c_int), ("rope_theta", C.c_float), ("rms_eps", C.c_float)]
+
+
 class FvhdTensor(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("dtype", C.c_int), ("numel", C.c_int64)]
 
@@ -63,6 +68,11 @@ SYMBOLS = {
                              C.c_int, C.c_int, C.c_int, C.c_int]),
     "fvhd_convffn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_int, C.c_void_p]),
+    "fvhd_llm_load": (C.c_int, [C.c_void_p, C.POINTER(FvhdLlmConfig), C.POINTER(C.c_void_p), C.c_int]),
+    "fvhd_llm_input": (C.c_void_p, [C.c_void_p]),
+    "fvhd_llm_prefill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "fvhd_llm_kv_cache": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "fvhd_llm_launches": (C.c_int, [C.c_void_p, C.c_int]),
 }
 
 
