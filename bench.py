@@ -250,6 +250,23 @@ def kernel_table(eng, images, flush, reps=5):
     return ktab, gk
 
 
+CONV_KERNELS = ("repmixer_tz_kernel", "repmixer_tc_kernel", "repmixer_dw_kernel", "stem2_kernel", "stem_kernel", "dwconv_kernel")
+
+
+def conv_roofline(ktab, peaks, peak_src):
+    """north_star (i): the conv-stage kernels (stem, RepMixer depthwise pair, PatchEmbed / RepCPE depthwise convs) against the HBM roof:
+    algorithmic bytes (inputs read once + outputs written once, `fvhd_step_info`) / live CUDA-event time."""
+    rows = [k for k in ktab if k["kernel"].startswith(CONV_KERNELS) and k["ms"] > 0 and k["gbs"]]
+    if not rows:
+        return None
+    ms = sum(k["ms"] for k in rows)
+    gb = sum(k["gbs"] * k["ms"] for k in rows) / 1e3          # GB/s * ms = MB
+    peak = float(peaks.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"]))
+    return {"bound": "hbm", "kernels": sorted({k["kernel"] for k in rows}), "achieved": round(gb * 1e3 / ms, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(gb * 1e3 / ms / peak, 4), "peak_source": f"{peak_src} (copy bandwidth)", "ms": round(ms, 4),
+            "per_kernel_frac": {k["kernel"]: round(k["gbs"] / peak, 4) for k in rows}}
+
+
 def roofline_obj(gk, peaks, peak_src, traffic=None, traffic_src=None):
     ach = gk["flops"] / gk["ms"] / 1e9
     peak = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
@@ -515,6 +532,7 @@ def run_gpu_arm(args):
             bp = min(CONFIG4_PASS, nb4)
             ktab4, gk4 = kernel_table(eng4, shard[:bp], flush, reps=2)
             cfg4["roofline"] = roofline_obj(gk4, peaks, peak_src)
+            cfg4["conv_roofline"] = conv_roofline(ktab4, peaks, peak_src)
             cfg4["kernels"] = ktab4
         del eng4, shard, out4
         torch.cuda.empty_cache()
@@ -575,7 +593,7 @@ def run_gpu_arm(args):
             "e2e": {"value": world * B * steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": host_img.numel() * 2,
                     "d2h_bytes_per_step": host_out.numel() * 2, "ms_per_step": e2e_ms / steps,
                     "api": "fvhd_encode_images_host (C ABI) via Engine.encode_images_host"},
-            "roofline": roofline, "whole_step": whole, "kernels": ktab,
+            "roofline": roofline, "conv_roofline": conv_roofline(ktab, peaks, peak_src), "whole_step": whole, "kernels": ktab,
             "step_ms_min": min(step_ms), "step_ms_median": statistics.median(step_ms),
             "sustained": {"seconds": sus_ms / 1e3, "forwards": n_sus, "images_per_s": world * B * n_sus / (sus_ms / 1e3),
                           "note": "back-to-back forwards, no L2 flush, no host sync between launches of a group of 20"},

@@ -1126,7 +1126,7 @@ void llm_free(LlmState* L) {
     for (void* b : bufs) if (b) cudaFree(b);
 }
 
-// Launch sequence of one L-token prefill: per layer RMSNorm, qkv GEMM (+bias), RoPE (+KV cache), causal GQA attention, o GEMM (+residual),
+// Launch sequence of one L-token prefill: per layer RMSNorm, qkv GEMM (+bias), RoPE + KV cache + causal GQA attention (one kernel), o GEMM (+residual),
 // RMSNorm, gate/up GEMM, SwiGLU, down GEMM (+residual); then final RMSNorm on the last row, lm_head GEMM (M = 1), argmax.
 int build_llm_plan(fvhd_handle h, LlmState* S, int L, Plan& pl) {
     const fvhd_llm_config& c = S->c;
@@ -1157,13 +1157,10 @@ int build_llm_plan(fvhd_handle h, LlmState* S, int L, Plan& pl) {
                "rmsnorm_kernel", 0, 0.0, 4.0 * L * H);
         if ((rc = add_gemm_l(xn, H, w[1], w[2], nullptr, qkv, L, NQ, H)) != FVHD_OK) return rc;
         const int heads = c.heads, kvh = c.kv_heads;
-        const int rgrid = (int)std::min<long>(((long)L * (heads + kvh) * (D / 2) + 255) / 256, 1184);
-        pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t { return launch_k(rope_kv_kernel, dim3(rgrid), dim3(256), 0, s, qkv, rope, kc, vc, L, heads, kvh, D); },
-               "rope_kv_kernel", 0, 0.0, 4.0 * L * NQ);
         const dim3 agrid((L + 31) / 32, heads);
         pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
-                   if (D == 64) return launch_k(causal_attn_kernel<64>, agrid, dim3(256), LlmAttnSmem<64>::BYTES, s, (const bf16*)qkv, att, L, heads, kvh, sl2);
-                   return launch_k(causal_attn_kernel<128>, agrid, dim3(256), LlmAttnSmem<128>::BYTES, s, (const bf16*)qkv, att, L, heads, kvh, sl2);
+                   if (D == 64) return launch_k(causal_attn_kernel<64>, agrid, dim3(256), LlmAttnSmem<64>::BYTES, s, (const bf16*)qkv, att, rope, kc, vc, L, heads, kvh, sl2);
+                   return launch_k(causal_attn_kernel<128>, agrid, dim3(256), LlmAttnSmem<128>::BYTES, s, (const bf16*)qkv, att, rope, kc, vc, L, heads, kvh, sl2);
                }, "causal_attn_kernel", 0, 2.0 * (double)L * L * HD, 2.0 * L * (NQ + HD));
         if ((rc = add_gemm_l(att, HD, w[3], nullptr, xc, xx, L, H, HD)) != FVHD_OK) return rc;
         const bf16* x2 = xx;

@@ -4,8 +4,8 @@
 // the glue kernels a Qwen2 layer needs around them:
 //     rmsnorm_kernel        Qwen2RMSNorm: y = w * x * rsqrt(mean(x^2) + eps)                        (modeling_qwen2.py Qwen2RMSNorm.forward)
 //     rope_table_kernel     cos / sin of pos * theta^(-2d/D), fp32, built once per handle          (Qwen2RotaryEmbedding)
-//     rope_kv_kernel        rotate_half RoPE in place on the q and k heads of the fused qkv rows; K / V rows copied to the KV cache
-//     causal_attn_kernel<D> causal GQA attention, flash-style over 64-key tiles, fp32 softmax / accumulation on the FMA pipes
+//     causal_attn_kernel<D> rotate_half RoPE on q and k (table lookups while the tiles are staged), K (post-RoPE) / V rows -> KV cache,
+//                           causal GQA attention, flash-style over 64-key tiles, fp32 softmax / accumulation on the FMA pipes
 //                           (L = 287 tokens x 14 heads: 0.3 GFLOP per layer -- latency, not throughput, matters here)
 //     silu_mul_kernel       SwiGLU gate: h = silu(gate) * up                                         (Qwen2MLP.forward)
 //     argmax_kernel         first token = argmax of the last position's logits
@@ -57,45 +57,17 @@ __global__ void rope_table_kernel(float2* __restrict__ table, int max_pos, int h
     table[i] = make_float2(c, s);
 }
 
-// qkv rows [L, (heads + 2 kv) * D]: rotate_half RoPE on the q and k heads (positions 0..L-1), in place; K and V rows -> cache (optional)
-__global__ void __launch_bounds__(256)
-rope_kv_kernel(bf16* __restrict__ qkv, const float2* __restrict__ table, bf16* __restrict__ k_cache, bf16* __restrict__ v_cache,
-               int L, int heads, int kv_heads, int D) {
-    pdl_launch_dependents();
-    pdl_wait();
-    const int half = D / 2;
-    const int ld = (heads + 2 * kv_heads) * D;
-    const int per_tok = (heads + kv_heads) * half;
-    const long total = (long)L * per_tok;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int tok = (int)(i / per_tok), r = (int)(i - (long)tok * per_tok);
-        const int hd = r / half, d = r - hd * half;                 // hd < heads: q head; else k head
-        bf16* p = qkv + (size_t)tok * ld + (size_t)hd * D + d;
-        const float2 cs = table[(size_t)tok * half + d];
-        const float x1 = __bfloat162float(p[0]), x2 = __bfloat162float(p[half]);
-        const bf16 o1 = __float2bfloat16_rn(x1 * cs.x - x2 * cs.y), o2 = __float2bfloat16_rn(x2 * cs.x + x1 * cs.y);
-        p[0] = o1; p[half] = o2;
-        if (k_cache && hd >= heads) {
-            bf16* kc = k_cache + ((size_t)tok * kv_heads + (hd - heads)) * D + d;
-            kc[0] = o1; kc[half] = o2;
-        }
-    }
-    if (v_cache) {
-        const long nv = (long)L * kv_heads * D;
-        for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long)gridDim.x * blockDim.x) {
-            const int tok = (int)(i / (kv_heads * D)), r = (int)(i - (long)tok * kv_heads * D);
-            v_cache[i] = qkv[(size_t)tok * ld + (size_t)(heads + kv_heads) * D + r];
-        }
-    }
-}
-
 template <int D> struct LlmAttnSmem { static constexpr size_t BYTES = (size_t)2 * 64 * (D + 8) * 2 + (size_t)32 * D * 4; };
 
-// Causal grouped-query attention over RoPE'd qkv rows.  grid (ceil(L / 32), heads); 8 warps x 4 queries; 64-key tiles in smem.
+// Causal grouped-query attention over the fused qkv rows [L, (heads + 2 kv) * D] (q heads, k heads, v heads), positions 0..L-1.
+// RoPE (rotate_half: pairs (d, d + D/2), Qwen2 apply_rotary_pos_emb) is applied while q and the K tiles are staged; the rotated K is
+// rounded to bf16 as the reference's bf16 tensors are.  The CTAs of the LAST query block of each group's first q head walk every key
+// tile: they also write K (post-RoPE) and V into the KV cache.  grid (ceil(L / 32), heads); 8 warps x 4 queries; 64-key tiles in smem.
 // out [L, heads * D] bf16.  scale_log2 = D^-0.5 * log2(e).
 template <int D>
 __global__ void __launch_bounds__(256)
-causal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int heads, int kv_heads, float scale_log2) {
+causal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const float2* __restrict__ rope, bf16* __restrict__ k_cache,
+                   bf16* __restrict__ v_cache, int L, int heads, int kv_heads, float scale_log2) {
     constexpr int TK = 64, QB = 32, NQ = 4, KP = D + 8;          // key pitch (halves): +16 B keeps the 16-B row reads conflict-free
     constexpr int DW = D / 64;                                   // bf16x2 words of V / o per lane
     extern __shared__ __align__(16) uint8_t attn_smem[];         // LlmAttnSmem<D>::BYTES
@@ -107,14 +79,21 @@ causal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, 
     const int hq = blockIdx.y, hk = hq / (heads / kv_heads);
     const int q0 = blockIdx.x * QB;
     const int ld = (heads + 2 * kv_heads) * D;
+    constexpr int HALF = D / 2;
+    const bool write_cache = k_cache != nullptr && blockIdx.x == gridDim.x - 1 && hq % (heads / kv_heads) == 0;
     pdl_wait();
-    // this CTA's queries, pre-scaled, fp32
-    for (int i = threadIdx.x; i < QB * D / 2; i += 256) {
-        const int qi = i / (D / 2), dp = i - qi * (D / 2);
-        float2 v = make_float2(0.f, 0.f);
-        if (q0 + qi < L) v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qkv + (size_t)(q0 + qi) * ld + (size_t)hq * D + 2 * dp));
-        Qs[qi * D + 2 * dp] = v.x * scale_log2;
-        Qs[qi * D + 2 * dp + 1] = v.y * scale_log2;
+    // this CTA's queries: RoPE, pre-scaled, fp32
+    for (int i = threadIdx.x; i < QB * HALF; i += 256) {
+        const int qi = i / HALF, d = i - qi * HALF;
+        float x1 = 0.f, x2 = 0.f;
+        float2 cs = make_float2(1.f, 0.f);
+        if (q0 + qi < L) {
+            const bf16* qp = qkv + (size_t)(q0 + qi) * ld + (size_t)hq * D + d;
+            x1 = __bfloat162float(qp[0]); x2 = __bfloat162float(qp[HALF]);
+            cs = rope[(size_t)(q0 + qi) * HALF + d];
+        }
+        Qs[qi * D + d] = (x1 * cs.x - x2 * cs.y) * scale_log2;
+        Qs[qi * D + d + HALF] = (x2 * cs.x + x1 * cs.y) * scale_log2;
     }
     float m[NQ], l[NQ], o[NQ][2 * DW];
 #pragma unroll
@@ -127,16 +106,35 @@ causal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, 
     const int qw = q0 + warp * NQ;                               // this warp's first query
     for (int k0 = 0; k0 <= q_last; k0 += TK) {
         __syncthreads();                                         // previous tile consumed (and Qs written)
-        for (int i = threadIdx.x; i < TK * D / 8; i += 256) {
-            const int kj = i / (D / 8), c = i - kj * (D / 8);
-            uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < TK * D / 16; i += 256) {       // one thread: the 8-wide chunk c and its rotation partner c + D/16
+            const int kj = i / (D / 16), c = i - kj * (D / 16);
+            uint4 ka = make_uint4(0, 0, 0, 0), kb = ka, va = ka, vb = ka;
             if (k0 + kj < L) {
                 const bf16* row = qkv + (size_t)(k0 + kj) * ld;
-                kv = *reinterpret_cast<const uint4*>(row + (size_t)(heads + hk) * D + c * 8);
-                vv = *reinterpret_cast<const uint4*>(row + (size_t)(heads + kv_heads + hk) * D + c * 8);
+                const bf16* kp = row + (size_t)(heads + hk) * D + c * 8;
+                const bf16* vp = row + (size_t)(heads + kv_heads + hk) * D + c * 8;
+                const uint4 k1 = *reinterpret_cast<const uint4*>(kp), k2 = *reinterpret_cast<const uint4*>(kp + HALF);
+                va = *reinterpret_cast<const uint4*>(vp); vb = *reinterpret_cast<const uint4*>(vp + HALF);
+                const float4* tb = reinterpret_cast<const float4*>(rope + (size_t)(k0 + kj) * HALF + c * 8);     // 8 (cos, sin) pairs
+                const uint32_t w1[4] = {k1.x, k1.y, k1.z, k1.w}, w2[4] = {k2.x, k2.y, k2.z, k2.w};
+                uint32_t o1[4], o2[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 t = tb[e];                                   // (cos, sin) of dims 2e and 2e + 1 of the chunk
+                    const float2 a = unpack_bf16x2(w1[e]), b = unpack_bf16x2(w2[e]);
+                    o1[e] = pack_bf16x2(a.x * t.x - b.x * t.y, a.y * t.z - b.y * t.w);
+                    o2[e] = pack_bf16x2(b.x * t.x + a.x * t.y, b.y * t.z + a.y * t.w);
+                }
+                ka = make_uint4(o1[0], o1[1], o1[2], o1[3]); kb = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+                if (write_cache) {
+                    bf16* kc = k_cache + ((size_t)(k0 + kj) * kv_heads + hk) * D + c * 8;
+                    bf16* vc = v_cache + ((size_t)(k0 + kj) * kv_heads + hk) * D + c * 8;
+                    *reinterpret_cast<uint4*>(kc) = ka; *reinterpret_cast<uint4*>(kc + HALF) = kb;
+                    *reinterpret_cast<uint4*>(vc) = va; *reinterpret_cast<uint4*>(vc + HALF) = vb;
+                }
             }
-            *reinterpret_cast<uint4*>(Ks + kj * KP + c * 8) = kv;
-            *reinterpret_cast<uint4*>(Vs + kj * KP + c * 8) = vv;
+            *reinterpret_cast<uint4*>(Ks + kj * KP + c * 8) = ka; *reinterpret_cast<uint4*>(Ks + kj * KP + c * 8 + HALF) = kb;
+            *reinterpret_cast<uint4*>(Vs + kj * KP + c * 8) = va; *reinterpret_cast<uint4*>(Vs + kj * KP + c * 8 + HALF) = vb;
         }
         __syncthreads();
         if (k0 > qw + NQ - 1) continue;                          // every key of the tile is in this warp's future (barriers stay uniform)

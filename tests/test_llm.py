@@ -64,7 +64,7 @@ def test_prefill_matches_hf_fp32(shape, lengths):
     m = _hf(*shape)
     H = shape[0]
     eng = pkg.LlmPrefill.from_hf(m, max_seq=max(lengths) + 8, device=dev)
-    assert eng.launches(lengths[0]) == shape[1] * 9 + 3
+    assert eng.launches(lengths[0]) == shape[1] * 8 + 3
     g = torch.Generator().manual_seed(11)
     for L in lengths:
         x = torch.randn(1, L, H, generator=g)
