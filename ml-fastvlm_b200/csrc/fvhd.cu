@@ -1157,10 +1157,10 @@ int build_llm_plan(fvhd_handle h, LlmState* S, int L, Plan& pl) {
                "rmsnorm_kernel", 0, 0.0, 4.0 * L * H);
         if ((rc = add_gemm_l(xn, H, w[1], w[2], nullptr, qkv, L, NQ, H)) != FVHD_OK) return rc;
         const int heads = c.heads, kvh = c.kv_heads;
-        const dim3 agrid((L + 31) / 32, heads);
+        const dim3 agrid((L + LLM_ATTN_QB - 1) / LLM_ATTN_QB, heads);
         pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
-                   if (D == 64) return launch_k(causal_attn_kernel<64>, agrid, dim3(256), LlmAttnSmem<64>::BYTES, s, (const bf16*)qkv, att, rope, kc, vc, L, heads, kvh, sl2);
-                   return launch_k(causal_attn_kernel<128>, agrid, dim3(256), LlmAttnSmem<128>::BYTES, s, (const bf16*)qkv, att, rope, kc, vc, L, heads, kvh, sl2);
+                   if (D == 64) return launch_k(causal_attn_kernel<64>, agrid, dim3(LLM_ATTN_THREADS), LlmAttnSmem<64>::BYTES, s, (const bf16*)qkv, att, rope, kc, vc, L, heads, kvh, sl2);
+                   return launch_k(causal_attn_kernel<128>, agrid, dim3(LLM_ATTN_THREADS), LlmAttnSmem<128>::BYTES, s, (const bf16*)qkv, att, rope, kc, vc, L, heads, kvh, sl2);
                }, "causal_attn_kernel", 0, 2.0 * (double)L * L * HD, 2.0 * L * (NQ + HD));
         if ((rc = add_gemm_l(att, HD, w[3], nullptr, xc, xx, L, H, HD)) != FVHD_OK) return rc;
         const bf16* x2 = xx;

@@ -10,7 +10,7 @@
 //     silu_mul_kernel       SwiGLU gate: h = silu(gate) * up                                         (Qwen2MLP.forward)
 //     argmax_kernel         first token = argmax of the last position's logits
 #pragma once
-#include "ptx.cuh"
+#include "mixer_tz.cuh"       // ffma2
 
 namespace fvhd {
 
@@ -57,18 +57,21 @@ __global__ void rope_table_kernel(float2* __restrict__ table, int max_pos, int h
     table[i] = make_float2(c, s);
 }
 
-template <int D> struct LlmAttnSmem { static constexpr size_t BYTES = (size_t)2 * 64 * (D + 8) * 2 + (size_t)32 * D * 4; };
+constexpr int LLM_ATTN_QB = 16;                 // queries per CTA: 4 warps x 4 queries (287 tokens x 14 heads -> 252 CTAs, two per SM)
+constexpr int LLM_ATTN_THREADS = 128;
+template <int D> struct LlmAttnSmem { static constexpr size_t BYTES = (size_t)2 * 64 * (D + 8) * 2 + (size_t)LLM_ATTN_QB * D * 4; };
 
 // Causal grouped-query attention over the fused qkv rows [L, (heads + 2 kv) * D] (q heads, k heads, v heads), positions 0..L-1.
 // RoPE (rotate_half: pairs (d, d + D/2), Qwen2 apply_rotary_pos_emb) is applied while q and the K tiles are staged; the rotated K is
 // rounded to bf16 as the reference's bf16 tensors are.  The CTAs of the LAST query block of each group's first q head walk every key
-// tile: they also write K (post-RoPE) and V into the KV cache.  grid (ceil(L / 32), heads); 8 warps x 4 queries; 64-key tiles in smem.
+// tile: they also write K (post-RoPE) and V into the KV cache.  grid (ceil(L / 16), heads); 4 warps x 4 queries; 64-key tiles in smem;
+// the dot products and the P V accumulation run as packed FFMA2 (two keys / two output dims per instruction).
 // out [L, heads * D] bf16.  scale_log2 = D^-0.5 * log2(e).
 template <int D>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(LLM_ATTN_THREADS)
 causal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const float2* __restrict__ rope, bf16* __restrict__ k_cache,
                    bf16* __restrict__ v_cache, int L, int heads, int kv_heads, float scale_log2) {
-    constexpr int TK = 64, QB = 32, NQ = 4, KP = D + 8;          // key pitch (halves): +16 B keeps the 16-B row reads conflict-free
+    constexpr int TK = 64, QB = LLM_ATTN_QB, NQ = 4, NT = LLM_ATTN_THREADS, KP = D + 8;   // key pitch (halves): +16 B keeps the 16-B row reads conflict-free
     constexpr int DW = D / 64;                                   // bf16x2 words of V / o per lane
     extern __shared__ __align__(16) uint8_t attn_smem[];         // LlmAttnSmem<D>::BYTES
     bf16* Ks = reinterpret_cast<bf16*>(attn_smem);
@@ -83,7 +86,7 @@ causal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const f
     const bool write_cache = k_cache != nullptr && blockIdx.x == gridDim.x - 1 && hq % (heads / kv_heads) == 0;
     pdl_wait();
     // this CTA's queries: RoPE, pre-scaled, fp32
-    for (int i = threadIdx.x; i < QB * HALF; i += 256) {
+    for (int i = threadIdx.x; i < QB * HALF; i += NT) {
         const int qi = i / HALF, d = i - qi * HALF;
         float x1 = 0.f, x2 = 0.f;
         float2 cs = make_float2(1.f, 0.f);
@@ -95,18 +98,19 @@ causal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const f
         Qs[qi * D + d] = (x1 * cs.x - x2 * cs.y) * scale_log2;
         Qs[qi * D + d + HALF] = (x2 * cs.x + x1 * cs.y) * scale_log2;
     }
-    float m[NQ], l[NQ], o[NQ][2 * DW];
+    float m[NQ], l[NQ];
+    float2 o[NQ][DW];                                             // output dims 2 (lane + 32 e), +1
 #pragma unroll
     for (int t = 0; t < NQ; ++t) {
         m[t] = -1e30f; l[t] = 0.f;
 #pragma unroll
-        for (int e = 0; e < 2 * DW; ++e) o[t][e] = 0.f;
+        for (int e = 0; e < DW; ++e) o[t][e] = make_float2(0.f, 0.f);
     }
     const int q_last = min(q0 + QB, L) - 1;
     const int qw = q0 + warp * NQ;                               // this warp's first query
     for (int k0 = 0; k0 <= q_last; k0 += TK) {
         __syncthreads();                                         // previous tile consumed (and Qs written)
-        for (int i = threadIdx.x; i < TK * D / 16; i += 256) {       // one thread: the 8-wide chunk c and its rotation partner c + D/16
+        for (int i = threadIdx.x; i < TK * D / 16; i += NT) {        // one thread: the 8-wide chunk c and its rotation partner c + D/16
             const int kj = i / (D / 16), c = i - kj * (D / 16);
             uint4 ka = make_uint4(0, 0, 0, 0), kb = ka, va = ka, vb = ka;
             if (k0 + kj < L) {
@@ -138,26 +142,27 @@ causal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const f
         }
         __syncthreads();
         if (k0 > qw + NQ - 1) continue;                          // every key of the tile is in this warp's future (barriers stay uniform)
-        // ---- scores: lane owns keys `lane` and `lane + 32` of the tile
-        float s[NQ][2];
+        // ---- scores: lane owns keys `lane` and `lane + 32` of the tile; one FFMA2 per (query, dim) covers both keys
+        float2 s[NQ];
 #pragma unroll
-        for (int t = 0; t < NQ; ++t) s[t][0] = s[t][1] = 0.f;
+        for (int t = 0; t < NQ; ++t) s[t] = make_float2(0.f, 0.f);
 #pragma unroll 2
         for (int c = 0; c < D / 8; ++c) {
             const uint4 ka = *reinterpret_cast<const uint4*>(Ks + lane * KP + c * 8);
             const uint4 kb = *reinterpret_cast<const uint4*>(Ks + (lane + 32) * KP + c * 8);
-            float fa[8], fb[8];
-            { float2 v;
-              v = unpack_bf16x2(ka.x); fa[0] = v.x; fa[1] = v.y; v = unpack_bf16x2(ka.y); fa[2] = v.x; fa[3] = v.y;
-              v = unpack_bf16x2(ka.z); fa[4] = v.x; fa[5] = v.y; v = unpack_bf16x2(ka.w); fa[6] = v.x; fa[7] = v.y;
-              v = unpack_bf16x2(kb.x); fb[0] = v.x; fb[1] = v.y; v = unpack_bf16x2(kb.y); fb[2] = v.x; fb[3] = v.y;
-              v = unpack_bf16x2(kb.z); fb[4] = v.x; fb[5] = v.y; v = unpack_bf16x2(kb.w); fb[6] = v.x; fb[7] = v.y; }
+            float2 kk[8];                                        // (key lane, key lane + 32) for the chunk's 8 dims
+            { const float2 a0 = unpack_bf16x2(ka.x), a1 = unpack_bf16x2(ka.y), a2 = unpack_bf16x2(ka.z), a3 = unpack_bf16x2(ka.w);
+              const float2 b0 = unpack_bf16x2(kb.x), b1 = unpack_bf16x2(kb.y), b2 = unpack_bf16x2(kb.z), b3 = unpack_bf16x2(kb.w);
+              kk[0] = make_float2(a0.x, b0.x); kk[1] = make_float2(a0.y, b0.y); kk[2] = make_float2(a1.x, b1.x); kk[3] = make_float2(a1.y, b1.y);
+              kk[4] = make_float2(a2.x, b2.x); kk[5] = make_float2(a2.y, b2.y); kk[6] = make_float2(a3.x, b3.x); kk[7] = make_float2(a3.y, b3.y); }
 #pragma unroll
             for (int t = 0; t < NQ; ++t) {
                 const float4 qa = *reinterpret_cast<const float4*>(Qs + (warp * NQ + t) * D + c * 8);
                 const float4 qb = *reinterpret_cast<const float4*>(Qs + (warp * NQ + t) * D + c * 8 + 4);
-                s[t][0] += qa.x * fa[0] + qa.y * fa[1] + qa.z * fa[2] + qa.w * fa[3] + qb.x * fa[4] + qb.y * fa[5] + qb.z * fa[6] + qb.w * fa[7];
-                s[t][1] += qa.x * fb[0] + qa.y * fb[1] + qa.z * fb[2] + qa.w * fb[3] + qb.x * fb[4] + qb.y * fb[5] + qb.z * fb[6] + qb.w * fb[7];
+                ffma2(s[t], kk[0], make_float2(qa.x, qa.x)); ffma2(s[t], kk[1], make_float2(qa.y, qa.y));
+                ffma2(s[t], kk[2], make_float2(qa.z, qa.z)); ffma2(s[t], kk[3], make_float2(qa.w, qa.w));
+                ffma2(s[t], kk[4], make_float2(qb.x, qb.x)); ffma2(s[t], kk[5], make_float2(qb.y, qb.y));
+                ffma2(s[t], kk[6], make_float2(qb.z, qb.z)); ffma2(s[t], kk[7], make_float2(qb.w, qb.w));
             }
         }
         // ---- online softmax per query, then o += P V
@@ -165,7 +170,7 @@ causal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const f
         for (int t = 0; t < NQ; ++t) {
             const int qi = qw + t;
             const bool a_ok = k0 + lane <= qi && k0 + lane < L, b_ok = k0 + lane + 32 <= qi && k0 + lane + 32 < L;
-            const float sa = a_ok ? s[t][0] : -1e30f, sb = b_ok ? s[t][1] : -1e30f;
+            const float sa = a_ok ? s[t].x : -1e30f, sb = b_ok ? s[t].y : -1e30f;
             float mx = fmaxf(sa, sb);
 #pragma unroll
             for (int of = 16; of > 0; of >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, of));
@@ -178,8 +183,8 @@ causal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const f
             m[t] = mn;
             l[t] = l[t] * corr + ps;
 #pragma unroll
-            for (int e = 0; e < 2 * DW; ++e) o[t][e] *= corr;
-            s[t][0] = pa; s[t][1] = pb;
+            for (int e = 0; e < DW; ++e) { o[t][e].x *= corr; o[t][e].y *= corr; }
+            s[t] = make_float2(pa, pb);
         }
 #pragma unroll 4
         for (int kj = 0; kj < 32; ++kj) {
@@ -191,11 +196,11 @@ causal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const f
             }
 #pragma unroll
             for (int t = 0; t < NQ; ++t) {
-                const float pa = __shfl_sync(0xffffffffu, s[t][0], kj), pb = __shfl_sync(0xffffffffu, s[t][1], kj);
+                const float pa = __shfl_sync(0xffffffffu, s[t].x, kj), pb = __shfl_sync(0xffffffffu, s[t].y, kj);
 #pragma unroll
                 for (int e = 0; e < DW; ++e) {
-                    o[t][2 * e] += pa * va[e].x + pb * vb[e].x;
-                    o[t][2 * e + 1] += pa * va[e].y + pb * vb[e].y;
+                    ffma2(o[t][e], va[e], make_float2(pa, pa));
+                    ffma2(o[t][e], vb[e], make_float2(pb, pb));
                 }
             }
         }
@@ -207,7 +212,7 @@ causal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const f
             const float inv = 1.f / l[t];
 #pragma unroll
             for (int e = 0; e < DW; ++e)
-                *reinterpret_cast<uint32_t*>(out + (size_t)qi * heads * D + (size_t)hq * D + 2 * (lane + 32 * e)) = pack_bf16x2(o[t][2 * e] * inv, o[t][2 * e + 1] * inv);
+                *reinterpret_cast<uint32_t*>(out + (size_t)qi * heads * D + (size_t)hq * D + 2 * (lane + 32 * e)) = pack_bf16x2(o[t][e].x * inv, o[t][e].y * inv);
         }
     }
 }
