@@ -1157,11 +1157,21 @@ int build_llm_plan(fvhd_handle h, LlmState* S, int L, Plan& pl) {
                "rmsnorm_kernel", 0, 0.0, 4.0 * L * H);
         if ((rc = add_gemm_l(xn, H, w[1], w[2], nullptr, qkv, L, NQ, H)) != FVHD_OK) return rc;
         const int heads = c.heads, kvh = c.kv_heads;
-        const dim3 agrid((L + LLM_ATTN_QB - 1) / LLM_ATTN_QB, heads);
-        pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
-                   if (D == 64) return launch_k(causal_attn_kernel<64>, agrid, dim3(LLM_ATTN_THREADS), LlmAttnSmem<64>::BYTES, s, (const bf16*)qkv, att, rope, kc, vc, L, heads, kvh, sl2);
-                   return launch_k(causal_attn_kernel<128>, agrid, dim3(LLM_ATTN_THREADS), LlmAttnSmem<128>::BYTES, s, (const bf16*)qkv, att, rope, kc, vc, L, heads, kvh, sl2);
-               }, "causal_attn_kernel", 0, 2.0 * (double)L * L * HD, 2.0 * L * (NQ + HD));
+        const char* attn_env = getenv("FVHD_LLM_ATTN");      // read when a plan (one per sequence length) is built
+        const bool attn_fma = attn_env && attn_env[0] == 'f';
+        if (attn_fma) {      // FVHD_LLM_ATTN=f: the FMA-pipe kernel (first version; kept for A/B)
+            const dim3 agrid((L + LLM_ATTN_QB - 1) / LLM_ATTN_QB, heads);
+            pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+                       if (D == 64) return launch_k(causal_attn_kernel<64>, agrid, dim3(LLM_ATTN_THREADS), LlmAttnSmem<64>::BYTES, s, (const bf16*)qkv, att, rope, kc, vc, L, heads, kvh, sl2);
+                       return launch_k(causal_attn_kernel<128>, agrid, dim3(LLM_ATTN_THREADS), LlmAttnSmem<128>::BYTES, s, (const bf16*)qkv, att, rope, kc, vc, L, heads, kvh, sl2);
+                   }, "causal_attn_kernel", 0, 2.0 * (double)L * L * HD, 2.0 * L * (NQ + HD));
+        } else {
+            const dim3 agrid((L + LLM_MMA_QB - 1) / LLM_MMA_QB, heads);
+            pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t {
+                       if (D == 64) return launch_k(causal_attn_mma_kernel<64>, agrid, dim3(LLM_MMA_THREADS), LlmAttnMmaSmem<64>::BYTES, s, (const bf16*)qkv, att, rope, kc, vc, L, heads, kvh, sl2);
+                       return launch_k(causal_attn_mma_kernel<128>, agrid, dim3(LLM_MMA_THREADS), LlmAttnMmaSmem<128>::BYTES, s, (const bf16*)qkv, att, rope, kc, vc, L, heads, kvh, sl2);
+                   }, "causal_attn_mma_kernel", 0, 2.0 * (double)L * L * HD, 2.0 * L * (NQ + HD));
+        }
         if ((rc = add_gemm_l(att, HD, w[3], nullptr, xc, xx, L, H, HD)) != FVHD_OK) return rc;
         const bf16* x2 = xx;
         pl.add([=](cudaStream_t s, const RunCtx&) -> cudaError_t { return launch_k(rmsnorm_kernel, dim3(ln_grid), dim3(256), 0, s, x2, xn, ln2, L, H, eps); },
@@ -1830,6 +1840,8 @@ int fvhd_llm_load(fvhd_handle h, const fvhd_llm_config* cfg, const void* const* 
     CUDA_TRY(h, cudaDeviceSynchronize());
     CUDA_TRY(h, set_smem(causal_attn_kernel<64>, LlmAttnSmem<64>::BYTES));
     CUDA_TRY(h, set_smem(causal_attn_kernel<128>, LlmAttnSmem<128>::BYTES));
+    CUDA_TRY(h, set_smem(causal_attn_mma_kernel<64>, LlmAttnMmaSmem<64>::BYTES));
+    CUDA_TRY(h, set_smem(causal_attn_mma_kernel<128>, LlmAttnMmaSmem<128>::BYTES));
     h->llm = S;
     return FVHD_OK;
 }

@@ -11,6 +11,7 @@
 //     argmax_kernel         first token = argmax of the last position's logits
 #pragma once
 #include "mixer_tz.cuh"       // ffma2
+#include "stem_attn_se.cuh"   // mma_bf16_16816, ldmatrix_x4_trans
 
 namespace fvhd {
 
@@ -214,6 +215,168 @@ causal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const f
             for (int e = 0; e < DW; ++e)
                 *reinterpret_cast<uint32_t*>(out + (size_t)qi * heads * D + (size_t)hq * D + 2 * (lane + 32 * e)) = pack_bf16x2(o[t][e].x * inv, o[t][e].y * inv);
         }
+    }
+}
+
+// The same attention on the tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate; flash-attention-2 register layout as in the tower's
+// attention_kernel): one warp = 16 queries, CTA = 2 warps = 32 queries x one head, 64-key tiles.  Q (RoPE'd, bf16) is staged once and
+// held as A fragments; S = Q K^T uses K rows as the col-major B operand, P V reads V through ldmatrix.trans.  ~27x fewer instructions
+// per query than the FMA-pipe kernel above (which stays selectable: FVHD_LLM_ATTN=f).
+constexpr int LLM_MMA_QB = 32, LLM_MMA_THREADS = 64;
+template <int D> struct LlmAttnMmaSmem { static constexpr size_t BYTES = (size_t)(2 * 64 + LLM_MMA_QB) * (D + 8) * 2; };
+
+template <int D>
+__global__ void __launch_bounds__(LLM_MMA_THREADS)
+causal_attn_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const float2* __restrict__ rope, bf16* __restrict__ k_cache,
+                       bf16* __restrict__ v_cache, int L, int heads, int kv_heads, float scale_log2) {
+    constexpr int TK = 64, QB = LLM_MMA_QB, NT = LLM_MMA_THREADS, KP = D + 8, HALF = D / 2, KS = D / 16, ND = D / 8;
+    extern __shared__ __align__(16) uint8_t attn_mma_smem[];
+    bf16* Ks = reinterpret_cast<bf16*>(attn_mma_smem);
+    bf16* Vs = Ks + TK * KP;
+    bf16* Qs = Vs + TK * KP;
+    pdl_launch_dependents();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int hq = blockIdx.y, hk = hq / (heads / kv_heads);
+    const int q0 = blockIdx.x * QB;
+    const int ld = (heads + 2 * kv_heads) * D;
+    const bool write_cache = k_cache != nullptr && blockIdx.x == gridDim.x - 1 && hq % (heads / kv_heads) == 0;
+    pdl_wait();
+    // ---- Q tile: RoPE, bf16 (as the reference's bf16 q), rows beyond L zero
+    for (int i = threadIdx.x; i < QB * HALF; i += NT) {
+        const int qi = i / HALF, d = i - qi * HALF;
+        float o1 = 0.f, o2 = 0.f;
+        if (q0 + qi < L) {
+            const bf16* qp = qkv + (size_t)(q0 + qi) * ld + (size_t)hq * D + d;
+            const float x1 = __bfloat162float(qp[0]), x2 = __bfloat162float(qp[HALF]);
+            const float2 cs = rope[(size_t)(q0 + qi) * HALF + d];
+            o1 = x1 * cs.x - x2 * cs.y; o2 = x2 * cs.x + x1 * cs.y;
+        }
+        Qs[qi * KP + d] = __float2bfloat16_rn(o1);
+        Qs[qi * KP + d + HALF] = __float2bfloat16_rn(o2);
+    }
+    __syncthreads();
+    const int qw = q0 + warp * 16;                               // this warp's first query
+    const int r0 = qw + g, r1 = qw + g + 8;
+    uint32_t qa[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        const bf16* qp = Qs + (warp * 16 + g) * KP + ks * 16 + t * 2;
+        qa[ks][0] = *reinterpret_cast<const uint32_t*>(qp);
+        qa[ks][1] = *reinterpret_cast<const uint32_t*>(qp + 8 * KP);
+        qa[ks][2] = *reinterpret_cast<const uint32_t*>(qp + 8);
+        qa[ks][3] = *reinterpret_cast<const uint32_t*>(qp + 8 * KP + 8);
+    }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float o[ND][4];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+
+    const int q_last = min(q0 + QB, L) - 1;
+    for (int k0 = 0; k0 <= q_last; k0 += TK) {
+        __syncthreads();                                         // previous tile consumed
+        for (int i = threadIdx.x; i < TK * D / 16; i += NT) {        // one thread: the 8-wide chunk c and its rotation partner c + D/16
+            const int kj = i / (D / 16), c = i - kj * (D / 16);
+            uint4 ka = make_uint4(0, 0, 0, 0), kb = ka, va = ka, vb = ka;
+            if (k0 + kj < L) {
+                const bf16* row = qkv + (size_t)(k0 + kj) * ld;
+                const bf16* kp = row + (size_t)(heads + hk) * D + c * 8;
+                const bf16* vp = row + (size_t)(heads + kv_heads + hk) * D + c * 8;
+                const uint4 k1 = *reinterpret_cast<const uint4*>(kp), k2 = *reinterpret_cast<const uint4*>(kp + HALF);
+                va = *reinterpret_cast<const uint4*>(vp); vb = *reinterpret_cast<const uint4*>(vp + HALF);
+                const float4* tb = reinterpret_cast<const float4*>(rope + (size_t)(k0 + kj) * HALF + c * 8);     // 8 (cos, sin) pairs
+                const uint32_t w1[4] = {k1.x, k1.y, k1.z, k1.w}, w2[4] = {k2.x, k2.y, k2.z, k2.w};
+                uint32_t o1[4], o2[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 tt = tb[e];
+                    const float2 a = unpack_bf16x2(w1[e]), b = unpack_bf16x2(w2[e]);
+                    o1[e] = pack_bf16x2(a.x * tt.x - b.x * tt.y, a.y * tt.z - b.y * tt.w);
+                    o2[e] = pack_bf16x2(b.x * tt.x + a.x * tt.y, b.y * tt.z + a.y * tt.w);
+                }
+                ka = make_uint4(o1[0], o1[1], o1[2], o1[3]); kb = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+                if (write_cache) {
+                    bf16* kc = k_cache + ((size_t)(k0 + kj) * kv_heads + hk) * D + c * 8;
+                    bf16* vc = v_cache + ((size_t)(k0 + kj) * kv_heads + hk) * D + c * 8;
+                    *reinterpret_cast<uint4*>(kc) = ka; *reinterpret_cast<uint4*>(kc + HALF) = kb;
+                    *reinterpret_cast<uint4*>(vc) = va; *reinterpret_cast<uint4*>(vc + HALF) = vb;
+                }
+            }
+            *reinterpret_cast<uint4*>(Ks + kj * KP + c * 8) = ka; *reinterpret_cast<uint4*>(Ks + kj * KP + c * 8 + HALF) = kb;
+            *reinterpret_cast<uint4*>(Vs + kj * KP + c * 8) = va; *reinterpret_cast<uint4*>(Vs + kj * KP + c * 8 + HALF) = vb;
+        }
+        __syncthreads();
+        if (k0 > qw + 15) continue;                              // every key of the tile lies in this warp's future (barriers stay uniform)
+        // ---- S = Q K^T for 64 keys
+        float s[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const bf16* kp = Ks + (j * 8 + g) * KP + ks * 16 + t * 2;
+                mma_bf16_16816(s[j], qa[ks], *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 8));
+            }
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int key = k0 + j * 8 + t * 2;                  // causal mask: key <= query row (and < L)
+            s[j][0] = (key <= r0 && key < L) ? s[j][0] * scale_log2 : -INFINITY;
+            s[j][1] = (key + 1 <= r0 && key + 1 < L) ? s[j][1] * scale_log2 : -INFINITY;
+            s[j][2] = (key <= r1 && key < L) ? s[j][2] * scale_log2 : -INFINITY;
+            s[j][3] = (key + 1 <= r1 && key + 1 < L) ? s[j][3] * scale_log2 : -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        // a row whose keys are all masked in this tile (k0 > row) keeps its state: its first tile (k0 = 0) always has key 0 unmasked
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float a0 = mn0 == -INFINITY ? 1.f : exp2f(m0 - mn0), a1 = mn1 == -INFINITY ? 1.f : exp2f(m1 - mn1);
+        m0 = mn0; m1 = mn1;
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s[j][0] = mn0 == -INFINITY ? 0.f : exp2f(s[j][0] - mn0); s[j][1] = mn0 == -INFINITY ? 0.f : exp2f(s[j][1] - mn0);
+            s[j][2] = mn1 == -INFINITY ? 0.f : exp2f(s[j][2] - mn1); s[j][3] = mn1 == -INFINITY ? 0.f : exp2f(s[j][3] - mn1);
+            rs0 += s[j][0] + s[j][1];
+            rs1 += s[j][2] + s[j][3];
+        }
+        l0 = l0 * a0 + rs0;
+        l1 = l1 * a1 + rs1;
+#pragma unroll
+        for (int i = 0; i < ND; ++i) { o[i][0] *= a0; o[i][1] *= a0; o[i][2] *= a1; o[i][3] *= a1; }
+        // ---- O += P V
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {          // 16 keys per step
+            uint32_t pa[4];
+            pa[0] = pack_bf16x2(s[2 * k2][0], s[2 * k2][1]);
+            pa[1] = pack_bf16x2(s[2 * k2][2], s[2 * k2][3]);
+            pa[2] = pack_bf16x2(s[2 * k2 + 1][0], s[2 * k2 + 1][1]);
+            pa[3] = pack_bf16x2(s[2 * k2 + 1][2], s[2 * k2 + 1][3]);
+#pragma unroll
+            for (int nt = 0; nt < ND; nt += 2) {   // two 8-wide dim tiles per ldmatrix.x4
+                const int mi = lane >> 3, r = lane & 7;
+                const int key = k2 * 16 + (mi & 1) * 8 + r;
+                const int dim0 = (nt + (mi >> 1)) * 8;
+                uint32_t vb[4];
+                ldmatrix_x4_trans(vb, Vs + key * KP + dim0);
+                mma_bf16_16816(o[nt], pa, vb[0], vb[1]);
+                mma_bf16_16816(o[nt + 1], pa, vb[2], vb[3]);
+            }
+        }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+#pragma unroll
+    for (int nt = 0; nt < ND; ++nt) {
+        const size_t c = (size_t)hq * D + nt * 8 + t * 2;
+        if (r0 < L) *reinterpret_cast<uint32_t*>(out + (size_t)r0 * heads * D + c) = pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
+        if (r1 < L) *reinterpret_cast<uint32_t*>(out + (size_t)r1 * heads * D + c) = pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
     }
 }
 

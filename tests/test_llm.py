@@ -90,3 +90,23 @@ def test_prefill_matches_hf_fp32(shape, lengths):
         # rerun: bit-identical (graph replay)
         tok2, logits2 = eng.prefill(L, want_logits=True)
         assert tok2 == tok and torch.equal(logits, logits2)
+
+
+@pytest.mark.gpu
+def test_fma_attention_variant_matches_mma():
+    """FVHD_LLM_ATTN=f selects the FMA-pipe attention kernel (first version); both kernels against each other on the same prefill."""
+    import os
+    dev = torch.device("cuda:0")
+    m = _hf(128, 2, 2, 1, 256, 512, seed=3)
+    x = torch.randn(70, 128, generator=torch.Generator().manual_seed(5)).to(torch.bfloat16)
+    outs = []
+    for env in (None, "f"):
+        if env:
+            os.environ["FVHD_LLM_ATTN"] = env
+        try:
+            eng = pkg.LlmPrefill.from_hf(m, max_seq=80, device=dev)
+            eng.input(70).copy_(x.to(dev))
+            outs.append(eng.prefill(70, want_logits=True)[1].float().cpu())
+        finally:
+            os.environ.pop("FVHD_LLM_ATTN", None)
+    assert rel_l2(outs[0], outs[1]) < 8e-3 and not torch.equal(outs[0], outs[1])      # different kernels, same result up to bf16 rounding of P
