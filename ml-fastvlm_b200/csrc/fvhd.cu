@@ -593,7 +593,7 @@ GemmCfg pick_gemm_cfg(int M, int N, int K, int act, int num_sms, bool allow_spli
                 const long cost = rounds * (tile + 400);
                 if (best.cost < 0 || cost < best.cost) best = GemmCfg{bn, cs, share_b, cost, 1};
                 // split-K variant (weight-streaming regime): S k-slices per tile, one work item per CTA, distributed reduction;
-                // overhead = fp32 partial tile written + re-read (at the same ~36 B/clk) + the arrival wait
+                // overhead = fp32 partial tile written + re-read (at the same ~36 B/clk) + the arrival wait (measured)
                 if (allow_split && cs == 1 && 2 * ctiles <= num_sms && num_kb >= 8) {
                     int S = num_sms / (int)ctiles;
                     if (S > num_kb / 4) S = num_kb / 4;
@@ -602,7 +602,9 @@ GemmCfg pick_gemm_cfg(int M, int N, int K, int act, int num_sms, bool allow_spli
                         const int kbs = (num_kb + S - 1) / S;
                         S = (num_kb + kbs - 1) / kbs;
                         const long ld_s = (long)kbs * bytes_kb / 36, mma_s = (long)kbs * 4 * (128 * bn / 256);
-                        const long cost_s = (ld_s > mma_s ? ld_s : mma_s) + 400 + 2 * (128L * bn * 4 / 36) + 2000;
+                        // + 11 k cycles: publish -> all-slices-arrived -> re-read, measured with tools/gemm_trace.py llm (MMAs done -> epilogue
+                        // done: 6.6 us for M 287 N 896 K 896 S 3, 9.5 us for K 4864 S 7; 1 us was assumed before)
+                        const long cost_s = (ld_s > mma_s ? ld_s : mma_s) + 400 + 2 * (128L * bn * 4 / 36) + 11000;
                         if (cost_s < best.cost) best = GemmCfg{bn, 1, 0, cost_s, S};
                     }
                 }

@@ -16,11 +16,15 @@ def main():
     g = torch.Generator().manual_seed(0)
     shapes = [("s2.fc1", 4096, 1536, 384, 1), ("s2.fc2", 4096, 384, 1536, 0), ("s1.fc1", 16384, 768, 192, 1), ("s1.fc2", 16384, 192, 768, 0),
               ("s0.fc1", 65536, 384, 96, 1), ("s3.proj", 1024, 768, 768, 0), ("proj2", 256, 896, 896, 0)]
+    variants = [(0, 1), (0, 4), (128, 1), (256, 1), (64, 1)]
+    if len(sys.argv) > 1 and sys.argv[1] == "llm":      # the four GEMMs of a Qwen2-0.5B layer at 287 tokens + lm_head, cost-model configuration
+        shapes = [("qkv", 287, 1152, 896, 0), ("o", 287, 896, 896, 0), ("gate_up", 287, 9728, 896, 0), ("down", 287, 896, 4864, 0), ("lm_head", 1, 151936, 896, 0)]
+        variants = [(0, 1), (128, 1), (256, 1)]
     for name, M, N, K, act in shapes:
         A = torch.randn(M, K, generator=g).to(torch.bfloat16).to(dev)
         W = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(dev)
         b = torch.randn(N, generator=g).to(dev)
-        for bn, cs in [(0, 1), (0, 4), (128, 1), (256, 1), (64, 1)]:
+        for bn, cs in variants:
             if bn and N % bn:
                 continue
             buf = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
