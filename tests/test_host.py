@@ -164,3 +164,54 @@ def test_checkpoint_ingest_released_layout(tmp_path, tower_sd, proj_sd):
     assert torch.equal(proj.state_dict()["2.weight"], proj_sd["2.weight"])
     with pytest.raises((KeyError, FileNotFoundError)):
         pkg.read_state_dicts(str(tmp_path / "nope"))
+
+
+def test_toeplitz_mixer_index_arithmetic():
+    """Host-side restatement of the address arithmetic of mixer_tz.cuh (no GPU): the 640-byte Toeplitz tile [P Q 0 P Q] with LBO = 2 blocks,
+    the no-swizzle K-major plane layout [8-col chunk][row][8] with the tap row as a start-address offset, the three K-steps with their
+    output windows (N = 16 / 24 / 8 at columns 0 / 8 / 24) and the shared zero chunk behind the last K-step -- emulated as the tensor
+    core reads them (element (m, k) of an operand = start + (m / 8) SBO + (m % 8) 16 B + (k / 8) LBO + (k % 8) 2 B) -- reproduce the 7 x 7
+    depthwise convolution of a 70 x 38 plane exactly."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    YR, CH, PLS, BT = 70, 1120, 5616, 640
+    OFF_PL, OFF_ZERO, OFF_B = 94464, 184320, 185472
+    NCHAN = 2
+    mem = np.full(120000, np.nan)                                  # one entry per 2-byte element; NaN = never written (must never be read)
+    el = lambda addr: addr // 2
+    w7 = rng.standard_normal((NCHAN, 7, 7))
+    mem[el(OFF_ZERO):el(OFF_ZERO + 1152)] = 0
+    mem[el(OFF_B):el(OFF_B + NCHAN * 7 * BT)] = 0
+    for idx in range(NCHAN * 7 * 64):                              # the kernel's tile-building loop
+        b, a, t = idx & 7, (idx >> 3) & 7, idx >> 6
+        c, dy = divmod(t, 7)
+        tile = OFF_B + t * BT + a * 16 + b * 2
+        dp, dq = 8 - (a - b), b - a
+        if 1 <= dp <= 6:
+            mem[el(tile)] = mem[el(tile + 3 * 128)] = w7[c, dy, dp]
+        if 0 <= dq <= 6:
+            mem[el(tile + 128)] = mem[el(tile + 4 * 128)] = w7[c, dy, dq]
+    y = rng.standard_normal((NCHAN, 70, 40))
+    y[:, :, 38:] = 0                                               # phase 1 zeroes the two padding columns of chunk 4
+    for c in range(NCHAN):
+        for ch in range(5):
+            for r in range(70):
+                base = el(OFF_PL + c * PLS + ch * CH + r * 16)
+                mem[base:base + 8] = y[c, r, ch * 8:ch * 8 + 8]
+
+    def operand(start, rows, lbo):                                 # [rows, 16] matrix as the tensor core gathers it
+        m = np.arange(rows)[:, None]
+        k = np.arange(16)[None, :]
+        return mem[el(start + (m // 8) * 128 + (m % 8) * 16 + (k // 8) * lbo + (k % 8) * 2)]
+
+    for c in range(NCHAN):
+        D = np.zeros((64, 32))
+        a_base, b_base = OFF_PL + c * PLS, OFF_B + c * 7 * BT
+        for dy in range(7):
+            D[:, 0:16] += operand(a_base + dy * 16, 64, CH) @ operand(b_base + 128 + dy * BT, 16, 256).T
+            D[:, 8:32] += operand(a_base + 2 * CH + dy * 16, 64, CH) @ operand(b_base + dy * BT, 24, 256).T
+            a2 = a_base + 4 * CH
+            D[:, 24:32] += operand(a2 + dy * 16, 64, OFF_ZERO - a2) @ operand(b_base + dy * BT, 8, 256).T
+        assert np.isfinite(D).all()                                # no operand element came from unwritten memory
+        ref = sum(y[c, dy:dy + 64, dx:dx + 32] * w7[c, dy, dx] for dy in range(7) for dx in range(7))
+        assert np.abs(D - ref).max() < 1e-12
