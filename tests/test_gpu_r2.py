@@ -544,3 +544,29 @@ def test_default_plan_picks_mixer_per_launch(packed, dev):
     k4 = [s["kernel"] for s in eng.steps(4)]
     assert k1.count("repmixer_tz_kernel") == 14 and k1.count("repmixer_tc_kernel") == 24, (k1.count("repmixer_tz_kernel"), k1.count("repmixer_tc_kernel"))
     assert k4.count("repmixer_tz_kernel") == 38 and "repmixer_tc_kernel" not in k4
+
+
+# ------------------------------------------------------------------ row f4 on the GPU: released-layout checkpoint -> drop-in modules
+def test_released_layout_checkpoint_runs_on_gpu(tmp_path, tower_sd, proj_sd, dev):
+    """A released-style folder (sharded safetensors with `model.vision_tower.*` / `model.mm_projector.*` keys among LLM tensors,
+    config.json) -> `load_pretrained` -> the drop-in tower + projector on the GPU: `encode_images` (the reference's two calls,
+    llava_arch.py:141-144) matches the oracle run on the same state dicts."""
+    import json
+    from safetensors.torch import save_file
+    full = {("model.vision_tower." + k): v.contiguous() for k, v in tower_sd.items()}
+    full.update({("model.mm_projector." + k): v.contiguous() for k, v in proj_sd.items()})
+    full["model.embed_tokens.weight"] = torch.zeros(8, 896)
+    keys = list(full.keys())
+    half = len(keys) // 2
+    save_file({k: full[k] for k in keys[:half]}, str(tmp_path / "model-00001-of-00002.safetensors"))
+    save_file({k: full[k] for k in keys[half:]}, str(tmp_path / "model-00002-of-00002.safetensors"))
+    json.dump({"mm_vision_tower": "mobileclip_l_256", "hidden_size": 896, "mm_hidden_size": 3072, "mm_projector_type": "mlp2x_gelu"},
+              open(tmp_path / "config.json", "w"))
+    tower, proj, cfg = pkg.load_pretrained(str(tmp_path), device=dev, dtype=torch.float16)
+    x = fx.synthetic_images(2, 256, seed=5)
+    ref = orc.encode_images(x, tower_sd, proj_sd)
+    with torch.no_grad():
+        feats = proj(tower(x.to(dev).half()))                       # the reference's encode_images body, module by module
+        fused = tower.encode_with_projector(x.to(dev).half(), proj)  # the one-call path encode_images takes (glue.py)
+    assert feats.dtype == torch.float16 and tuple(feats.shape) == (2, 16, 896)
+    assert rel_l2(feats.float(), ref) < E2E_TOL and rel_l2(fused.float(), ref) < E2E_TOL
