@@ -26,6 +26,13 @@
 //   warps 2-5   epilogue: TMEM -> +b7 -> bf16 -> staging tile [col][row][8 ch] (reuses the plane buffer the MMAs just released;
 //               channels c and c + 4 share a sub-partition, so a thread packs 4 channels = one 8-byte store, and the column-major
 //               tile makes those stores conflict-free) -> one TMA store per tile column (64 rows x 16 B, no LSU traffic)
+//
+// Every global access of this kernel is a 16-byte piece (8 channels) of a 32-byte sector whose other half belongs to the neighbouring
+// channel group, i.e. to ANOTHER CTA.  Measured: whenever the two drift apart (staggered CTA starts under programmatic dependent launch
+// were enough), half-written / half-read sectors leave the L2 and the kernel -- and its successor -- slow down by up to 1.6x.  The two
+// sibling groups are therefore launched as a 2-CTA cluster and their TMA warps handshake once per item (two alternating mbarriers,
+// remote arrives; a final cluster barrier keeps a CTA alive while its sibling may still arrive on it): stage 0 at batch 32 went from
+// 770 to 493 us per launch.  Clusters of 4 / 8 lose more resident CTAs to GPC placement than they gain.
 #pragma once
 #include "gemm_tcgen05.cuh"
 
