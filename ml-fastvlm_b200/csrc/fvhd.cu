@@ -429,6 +429,7 @@ int ensure_cuda(fvhd_handle h) {
         }
     }
     CUDA_TRY(h, set_smem(dwconv_kernel<7, 1, 1, 0, 16, 16, 8>, DwCfg<7, 1, 1, 16, 16>::SMEM));
+    CUDA_TRY(h, set_smem(dwconv_kernel<7, 1, 1, 0, 8, 16, 8>, DwCfg<7, 1, 1, 8, 16>::SMEM));
     CUDA_TRY(h, set_smem(dwconv_kernel<7, 2, 2, 1, 8, 8, 4>, DwCfg<7, 2, 2, 8, 8>::SMEM));
     CUDA_TRY(h, set_smem(dwconv_kernel<3, 1, 2, 0, 16, 16, 8>, DwCfg<3, 1, 2, 16, 16>::SMEM));
     CUDA_TRY(h, set_smem(stem_kernel<float>, STEM_SMEM));
@@ -692,6 +693,14 @@ int make_dw_step(fvhd_handle h, Step* out_step, const bf16* in, bf16* out, const
         return launch_k(dwconv_kernel<KS, S, MULT, ACT, TOH, TOW, SW>, grid, dim3(DW_THREADS), smem, s, tm, out, w, b, H, W, C, Ho, Wo, tx);
     };
     return FVHD_OK;
+}
+
+// RepCPE / attention-block dw7x7 (stride 1): 16 x 16 tiles, or 8 x 16 tiles while 16 x 16 would leave SMs without a CTA (batch 1:
+// stage 3 has 96 such CTAs, stage 4 has 48) -- the launch is pure latency there and half the rows per CTA halve it.
+int make_dw7_step(fvhd_handle h, Step* out_step, const bf16* in, bf16* out, const float* w, const float* b, int batch, int H, int W, int C) {
+    const long ctas16 = (long)((W + 15) / 16) * ((H + 15) / 16) * (C / DW_CG) * batch;
+    if (ctas16 < h->num_sms && H > 8) return make_dw_step<7, 1, 1, 0, 8, 16, 8>(h, out_step, in, out, w, b, batch, H, W, C);
+    return make_dw_step<7, 1, 1, 0, 16, 16, 8>(h, out_step, in, out, w, b, batch, H, W, C);
 }
 
 const float* WF(fvhd_handle h, const std::string& n) { return reinterpret_cast<const float*>(h->wptr.at(n)); }
@@ -962,7 +971,7 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
             break;
         }
         case 3:     // RepCPE: dw7x7 + bias (identity folded into the centre tap)
-            { Step ds; if ((rc = make_dw_step<7, 1, 1, 0, 16, 16, 8>(h, &ds, in, out, WF(h, p + "dw.w"), WF(h, p + "dw.b"), batch, H, W, c)) != FVHD_OK) return rc; pl.add(ds, "dwconv_kernel<7,1,1>", U, 2.0 * Md * c * 49, 4.0 * Md * c); }
+            { Step ds; if ((rc = make_dw7_step(h, &ds, in, out, WF(h, p + "dw.w"), WF(h, p + "dw.b"), batch, H, W, c)) != FVHD_OK) return rc; pl.add(ds, "dwconv_kernel<7,1,1>", U, 2.0 * Md * c * 49, 4.0 * Md * c); }
             break;
         case 4: {   // AttentionBlock
             const int N = H * W;
@@ -989,7 +998,7 @@ int build_plan(fvhd_handle h, int batch, Plan& pl) {
                 }, "attention_kernel", U, 4.0 * batch * (double)N * N * c, 8.0 * Md * c);
             }
             if ((rc = add_gemm(h, pl, U, t1, c, WB(h, p + "proj.w"), WF(h, p + "proj.b"), in, c, x1, c, M, c, c, 0)) != FVHD_OK) return rc;
-            { Step ds; if ((rc = make_dw_step<7, 1, 1, 0, 16, 16, 8>(h, &ds, x1, bf.Z, WF(h, p + "dw.w"), WF(h, p + "dw.b"), batch, H, W, c)) != FVHD_OK) return rc; pl.add(ds, "dwconv_kernel<7,1,1>", U, 2.0 * Md * c * 49, 4.0 * Md * c); }
+            { Step ds; if ((rc = make_dw7_step(h, &ds, x1, bf.Z, WF(h, p + "dw.w"), WF(h, p + "dw.b"), batch, H, W, c)) != FVHD_OK) return rc; pl.add(ds, "dwconv_kernel<7,1,1>", U, 2.0 * Md * c * 49, 4.0 * Md * c); }
             if ((rc = add_convffn_steps(h, pl, U, p, bf, bf.Z, x1, out, M, c)) != FVHD_OK) return rc;
             break;
         }
