@@ -215,3 +215,24 @@ def test_toeplitz_mixer_index_arithmetic():
         assert np.isfinite(D).all()                                # no operand element came from unwritten memory
         ref = sum(y[c, dy:dy + 64, dx:dx + 32] * w7[c, dy, dx] for dy in range(7) for dx in range(7))
         assert np.abs(D - ref).max() < 1e-12
+
+
+def test_bench_roofline_helpers():
+    """bench.py's roofline arithmetic on a hand-made kernel table (no GPU): tcgen05 group = FLOPs / time against the bf16 peak, conv
+    stages = algorithmic bytes / time against the HBM peak; both arms print the same `config` dict."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    peaks = {"hbm_gbs": 6000.0, "bf16_tflops": 1500.0}
+    ktab = [{"kernel": "repmixer_tz_kernel", "launches": 38, "ms": 2.0, "share": 0.5, "tflops": 40.0, "gbs": 2400.0},
+            {"kernel": "stem2_kernel", "launches": 1, "ms": 1.0, "share": 0.25, "tflops": 46.0, "gbs": 600.0},
+            {"kernel": "convffn_tcgen05_kernel", "launches": 38, "ms": 1.0, "share": 0.25, "tflops": 900.0, "gbs": 1200.0}]
+    cr = bench.conv_roofline(ktab, peaks, "measured")
+    assert cr["bound"] == "hbm" and cr["kernels"] == ["repmixer_tz_kernel", "stem2_kernel"]
+    assert abs(cr["achieved"] - (2400.0 * 2.0 + 600.0 * 1.0) / 3.0) < 0.1 and abs(cr["frac"] - 1800.0 / 6000.0) < 1e-3
+    gk = {"launches": 38, "ms": 1.0, "flops": 900e9, "names": ["convffn_tcgen05_kernel"], "sum_ms": 4.0}
+    rf = bench.roofline_obj(gk, peaks, "measured")
+    assert rf["bound"] == "tensor" and abs(rf["achieved"] - 900.0) < 1e-6 and abs(rf["frac"] - 0.6) < 1e-6 and rf["share_of_step"] == 0.25
+    assert bench.make_config(2, 1) == bench.make_config(2, 1) and bench.make_config(2, 1)["global_batch"] == 2
+    assert "convffn_tcgen05_kernel" in bench.TC_KERNELS and "attention_umma_kernel" in bench.TC_KERNELS
